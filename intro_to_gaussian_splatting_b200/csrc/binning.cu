@@ -1,0 +1,319 @@
+// binning.cu -- tile binning: single-pass prefix sum of tile counts, key emission, tile ranges.
+//
+// Replaces the per-tile boolean masks of GaussianScene.render_image
+// (splat/gaussian_scene.py:208-226): instead of an O(tiles*M) mask sweep, every in-view Gaussian is
+// expanded into one (key, payload) pair per tile of its rect,
+//     key = tile_id << 32 | float_as_uint(z_view),  tile_id = ty*tiles_x + tx,  payload = Gaussian index
+//  and the sorted key array is cut into per-tile [start,end) ranges.
+//
+// Roofline: HBM.  scan: 4 B read + 4 B written per Gaussian.  emit: 12 B written per key
+// (+ 24 B per Gaussian read).  ranges: 8 B read per key + 8 B per tile.
+#include "gsb_internal.cuh"
+
+namespace gsb {
+
+namespace {
+
+constexpr uint32_t kFlagShift = 30;
+constexpr uint32_t kFlagAggregate = 1u << kFlagShift;
+constexpr uint32_t kFlagPrefix = 2u << kFlagShift;
+constexpr uint32_t kValueMask = (1u << kFlagShift) - 1u;
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+}  // namespace
+
+size_t scan_status_words(int64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile) + 2; }
+
+// Decoupled look-back exclusive scan (one pass over the data).  status[0] is the ticket counter,
+// status[1 + b] the (flag | value) word of logical block b.
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
+            uint32_t* __restrict__ offsets, uint32_t* __restrict__ total, uint32_t* status) {
+  __shared__ uint32_t s_block;
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_excl;
+  if (threadIdx.x == 0) s_block = atomicAdd(&status[0], 1u);  // ticket: predecessors are already running
+  __syncthreads();
+  const uint32_t b = s_block;
+  uint32_t* st = status + 1;
+  const int64_t base = (int64_t)b * kScanTile + (int64_t)threadIdx.x * kScanItems;
+
+  uint32_t v[kScanItems];
+  uint32_t local = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    uint32_t c = 0;
+    if (i < n) c = perm ? count[perm[i]] : count[i];
+    v[k] = local;  // exclusive within the thread
+    local += c;
+  }
+  // block exclusive scan of the per-thread sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, block_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    uint32_t t = s_warp[w];
+    if (w < warp) warp_off += t;
+    block_sum += t;
+  }
+  const uint32_t thread_excl = warp_off + inc - local;
+
+  // publish the aggregate, then look back for the exclusive prefix of this block
+  if (warp == 0) {
+    uint32_t excl = 0;
+    if (b == 0) {
+      if (lane == 0) st_relaxed(&st[0], kFlagPrefix | block_sum);
+    } else {
+      if (lane == 0) st_relaxed(&st[b], kFlagAggregate | block_sum);
+      int64_t idx = (int64_t)b - 1;
+      while (true) {
+        int64_t j = idx - lane;
+        uint32_t s = kFlagPrefix;  // virtual block -1: inclusive prefix 0
+        if (j >= 0) {
+          s = ld_relaxed(&st[j]);
+          while ((s >> kFlagShift) == 0) s = ld_relaxed(&st[j]);
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, (s >> kFlagShift) == 2u);
+        if (pm) {
+          int first = __ffs(pm) - 1;
+          excl += warp_sum(lane <= first ? (s & kValueMask) : 0u);
+          break;
+        }
+        excl += warp_sum(s & kValueMask);
+        idx -= 32;
+      }
+      if (lane == 0) st_relaxed(&st[b], kFlagPrefix | (excl + block_sum));
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if ((int64_t)(b + 1) * kScanTile >= n) *total = excl + block_sum;
+    }
+  }
+  __syncthreads();
+  const uint32_t off = s_excl + thread_excl;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    if (i < n) offsets[i] = off + v[k];
+  }
+}
+
+int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* total,
+                uint32_t* status, cudaStream_t st) {
+  if (n == 0) return (int)cudaMemsetAsync(total, 0, 4, st);
+  unsigned blocks = (unsigned)((n + kScanTile - 1) / kScanTile);
+  scan_kernel<<<blocks, kScanThreads, 0, st>>>(count, perm, n, offsets, total, status);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// emit: output-parallel expansion.  A block owns 256 consecutive Gaussians (in emission order) and
+// walks ITS OUTPUT RANGE with coalesced stores; each output slot finds its Gaussian by binary search
+// over the block's 256 offsets in shared memory, so a Gaussian covering 2 000 tiles costs the same
+// per key as one covering 4.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmitThreads = 256;
+
+__global__ void __launch_bounds__(kEmitThreads)
+emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
+            int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect,
+            const uint32_t* __restrict__ count, int tiles_x, uint64_t* __restrict__ keys,
+            uint32_t* __restrict__ payload) {
+  __shared__ uint32_t s_off[kEmitThreads + 1];
+  __shared__ uint32_t s_gid[kEmitThreads];
+  __shared__ uint32_t s_depth[kEmitThreads];
+  __shared__ ushort4 s_rect[kEmitThreads];
+  const int64_t base = (int64_t)blockIdx.x * kEmitThreads;
+  const int64_t i = base + threadIdx.x;
+  uint32_t off = 0, g = 0;
+  if (i < n) {
+    g = perm ? perm[i] : (uint32_t)i;
+    off = offsets[i];
+    s_gid[threadIdx.x] = g;
+    s_depth[threadIdx.x] = depth_key[g];
+    s_rect[threadIdx.x] = rect[g];
+  }
+  const uint32_t k_total = *total;
+  s_off[threadIdx.x] = (i < n) ? off : k_total;
+  if (threadIdx.x == 0) {
+    int64_t nxt = base + kEmitThreads;
+    s_off[kEmitThreads] = (nxt < n) ? offsets[nxt] : k_total;
+  }
+  __syncthreads();
+  const uint32_t begin = s_off[0], end = s_off[kEmitThreads];
+  for (uint32_t o = begin + threadIdx.x; o < end; o += kEmitThreads) {
+    // largest j with s_off[j] <= o  (entries with count 0 share their successor's offset and lose)
+    int lo = 0, hi = kEmitThreads;  // invariant: s_off[lo] <= o < s_off[hi]
+#pragma unroll
+    for (int step = 0; step < 8; ++step) {
+      int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= o) lo = mid; else hi = mid;
+    }
+    const ushort4 r = s_rect[lo];
+    const uint32_t t = o - s_off[lo];
+    const uint32_t w = (uint32_t)r.y - (uint32_t)r.x + 1u;
+    const uint32_t ty = (uint32_t)r.z + t / w;
+    const uint32_t tx = (uint32_t)r.x + t % w;
+    const uint32_t tile = ty * (uint32_t)tiles_x + tx;
+    keys[o] = ((uint64_t)tile << 32) | (uint64_t)s_depth[lo];
+    payload[o] = s_gid[lo];
+  }
+  (void)count;
+}
+
+int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
+                const uint32_t* depth_key, const ushort4* rect, const uint32_t* count, int tiles_x,
+                uint64_t* keys, uint32_t* payload, cudaStream_t st) {
+  if (n == 0) return 0;
+  unsigned blocks = (unsigned)((n + kEmitThreads - 1) / kEmitThreads);
+  emit_kernel<<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, count, tiles_x, keys, payload);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile ranges: boundaries of the tile field in the sorted key array.  ranges must be zeroed
+// (empty tiles stay (0,0)).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ranges_kernel(const uint64_t* __restrict__ sorted_keys, int64_t k, uint2* __restrict__ ranges) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const uint32_t t = (uint32_t)(sorted_keys[i] >> 32);
+  const uint32_t tp = i > 0 ? (uint32_t)(sorted_keys[i - 1] >> 32) : 0xFFFFFFFFu;
+  if (i == 0 || tp != t) {
+    ranges[t].x = (uint32_t)i;
+    if (i > 0) ranges[tp].y = (uint32_t)i;
+  }
+  if (i == k - 1) ranges[t].y = (uint32_t)k;
+}
+
+int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k, uint2* ranges, cudaStream_t st) {
+  (void)total;
+  if (k == 0) return 0;
+  unsigned blocks = (unsigned)((k + 255) / 256);
+  ranges_kernel<<<blocks, 256, 0, st>>>(sorted_keys, k, ranges);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+int launch_iota(uint32_t* p, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);
+  return (int)cudaGetLastError();
+}
+
+// (H,W,3) -> (W,H,3): the layout GaussianScene.render_image returns (splat/gaussian_scene.py:206,:227)
+__global__ void hwc_to_whc_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H) {
+  __shared__ float tile[32][33 * 3];
+  int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int y = y0 + r;
+    for (int c = threadIdx.x; c < 96; c += blockDim.x) {
+      int x = x0 + c / 3;
+      if (x < W && y < H) tile[r][c] = src[((size_t)y * W + x0) * 3 + c];
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {  // r = x within tile
+    int x = x0 + r;
+    for (int c = threadIdx.x; c < 96; c += blockDim.x) {
+      int yy = c / 3, ch = c % 3;
+      int y = y0 + yy;
+      if (x < W && y < H) dst[((size_t)x * H + y0) * 3 + c] = tile[yy][r * 3 + ch];
+    }
+  }
+}
+int launch_hwc_to_whc(const float* src, float* dst, int W, int H, cudaStream_t st) {
+  dim3 grid((W + 31) / 32, (H + 31) / 32), block(32, 8);
+  hwc_to_whc_kernel<<<grid, block, 0, st>>>(src, dst, W, H);
+  return (int)cudaGetLastError();
+}
+
+__global__ void to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float v = fminf(fmaxf(src[i], 0.f), 1.f);
+    dst[i] = (uint8_t)__float2int_rn(v * 255.f);
+  }
+}
+int launch_to_u8(const float* src, uint8_t* dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+  return (int)cudaGetLastError();
+}
+
+// PreprocessedScene rows in depth order (gsb_preprocess): gather through `order`.
+__global__ void gather_preprocess_kernel(const uint32_t* __restrict__ order, int64_t m, const float4* __restrict__ rec,
+                                         const float* __restrict__ planes, int64_t n_pad,
+                                         const uint32_t* __restrict__ depth_key, DebugOut dbg, float* points_xy,
+                                         float* colors, float* cov2d, float* depths, float* conic, float* radius,
+                                         float* min_x, float* min_y, float* max_x, float* max_y, float* sig_op,
+                                         int32_t* src_index) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t g = order[j];
+  const float4 r0 = rec[3 * (size_t)g], r2 = rec[3 * (size_t)g + 2];
+  if (points_xy) { points_xy[2 * j] = r0.x; points_xy[2 * j + 1] = r0.y; }
+  if (colors) {
+    colors[3 * j] = planes[PR * n_pad + g];
+    colors[3 * j + 1] = planes[PG * n_pad + g];
+    colors[3 * j + 2] = planes[PB * n_pad + g];
+  }
+  if (depths) depths[j] = __uint_as_float(depth_key[g]);
+  if (radius) radius[j] = r2.y;
+  if (sig_op) sig_op[j] = r2.z;
+  if (src_index) src_index[j] = (int32_t)g;
+  if (cov2d) reinterpret_cast<float4*>(cov2d)[j] = reinterpret_cast<const float4*>(dbg.cov2d)[g];
+  if (conic) reinterpret_cast<float4*>(conic)[j] = reinterpret_cast<const float4*>(dbg.conic)[g];
+  const float4 bb = reinterpret_cast<const float4*>(dbg.bbox)[g];
+  if (min_x) min_x[j] = bb.x;
+  if (min_y) min_y[j] = bb.y;
+  if (max_x) max_x[j] = bb.z;
+  if (max_y) max_y[j] = bb.w;
+}
+
+int launch_gather_preprocess(const uint32_t* order, int64_t m, const float4* rec, const float* planes, int64_t n_pad,
+                             const uint32_t* depth_key, const DebugOut& dbg, float* points_xy, float* colors,
+                             float* cov2d, float* depths, float* conic, float* radius, float* min_x, float* min_y,
+                             float* max_x, float* max_y, float* sig_op, int32_t* src_index, cudaStream_t st) {
+  if (m == 0) return 0;
+  gather_preprocess_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(order, m, rec, planes, n_pad, depth_key, dbg,
+                                                                      points_xy, colors, cov2d, depths, conic, radius,
+                                                                      min_x, min_y, max_x, max_y, sig_op, src_index);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gsb

@@ -1,0 +1,198 @@
+// composite.cu -- per-tile front-to-back alpha compositing.
+//
+// Replaces GaussianScene.render_tile / render_pixel (splat/gaussian_scene.py:146-198) and
+// compute_gaussian_weight (splat/utils.py:357-365) [semantics REF_CPU, the parity target], and the
+// brute-force render_tile kernel of splat/c/render.cu:21-87 [semantics REF_CU].
+//
+// REF_CPU per (pixel, Gaussian) step, in list order (front to back):
+//     d = mean - pixel;  w = exp(-0.5 * d^T inv d);  alpha = w * sigmoid(sigmoid(logit))
+//     test = T * (1 - alpha);  if test < 1e-6: STOP, this Gaussian is NOT added
+//     C += T * alpha * c;  T = test
+// No per-pixel bbox test, no alpha clamp, no 1/255 skip.
+//
+// One CTA per 16x16 tile, one thread per pixel; each warp owns an 8x4 pixel block so that early
+// termination is spatially coherent.  The tile's instance list is staged through shared memory in
+// batches of 256: thread t gathers the 48-byte record of instance batch+t (prefetched into registers
+// one batch ahead, so the gather latency hides behind the blend loop), every thread then reads the
+// records as shared-memory broadcasts.  A warp leaves the blend loop when all its pixels are done; the
+// CTA stops fetching batches when __syncthreads_and says every pixel is done.
+//
+// Roofline: issue slots (fp32 FMA/ALU + MUFU.EX2), not HBM: ~20 warp-instructions per
+// (warp, Gaussian) step; HBM traffic is 4 B payload + 48 B record per instance + 12 B per pixel.
+#include "gsb_internal.cuh"
+
+namespace gsb {
+
+namespace {
+
+constexpr int kBatch = 256;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct CompositeArgs {
+  int width, height, tiles_x, tiles_y;
+  float min_weight, alpha_max;
+};
+
+template <int kSem>
+__global__ void __launch_bounds__(256)
+composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
+                 const float4* __restrict__ rec, const float4* __restrict__ bbox, float* __restrict__ image,
+                 const __grid_constant__ CompositeArgs a) {
+  __shared__ float4 s0[kBatch];  // mx, my, qa, qb
+  __shared__ float4 s1[kBatch];  // qc, op, r, g
+  __shared__ float s2[kBatch];   // b
+  __shared__ float4 s3[kSem == GSB_SEM_REF_CU ? kBatch : 1];  // bbox (REF_CU only)
+
+  const int tile = blockIdx.x;
+  const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int px = tx * kTile + (warp & 1) * 8 + (lane & 7);
+  const int py = ty * kTile + (warp >> 1) * 4 + (lane >> 3);
+  const bool inside = px < a.width && py < a.height;
+  const float fx = (float)px, fy = (float)py;
+
+  const uint2 rg = ranges[tile];
+  const uint32_t len = rg.y - rg.x;
+
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f;
+  bool done = !inside;
+
+  // register-staged prefetch of the first batch
+  float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
+  if ((uint32_t)tid < len) {
+    const uint32_t g = payload[rg.x + tid];
+    r0 = rec[3 * (size_t)g]; r1 = rec[3 * (size_t)g + 1]; r2 = rec[3 * (size_t)g + 2];
+    if (kSem == GSB_SEM_REF_CU) r3 = bbox[g];
+  }
+  for (uint32_t b0 = 0; b0 < len; b0 += kBatch) {
+    s0[tid] = r0; s1[tid] = r1; s2[tid] = r2.x;
+    if (kSem == GSB_SEM_REF_CU) s3[tid] = r3;
+    __syncthreads();
+    const uint32_t nxt = b0 + kBatch + tid;
+    if (nxt < len) {
+      const uint32_t g = payload[rg.x + nxt];
+      r0 = rec[3 * (size_t)g]; r1 = rec[3 * (size_t)g + 1]; r2 = rec[3 * (size_t)g + 2];
+      if (kSem == GSB_SEM_REF_CU) r3 = bbox[g];
+    }
+    const int cnt = (int)min((uint32_t)kBatch, len - b0);
+    if (!done) {
+#pragma unroll 4
+      for (int i = 0; i < cnt; ++i) {
+        const float4 g0 = s0[i];
+        const float4 g1 = s1[i];
+        if (kSem == GSB_SEM_REF_CU) {
+          const float4 bb = s3[i];
+          if (fx < bb.x || fx > bb.z || fy < bb.y || fy > bb.w) continue;
+        }
+        const float dx = g0.x - fx, dy = g0.y - fy;
+        const float p = dx * (g0.z * dx + g0.w * dy) + (g1.x * dy) * dy;
+        float alpha = ex2_approx(p) * g1.y;
+        if (kSem == GSB_SEM_REF_CU) alpha = fminf(a.alpha_max, alpha);
+        const float ta = T * alpha;
+        const float test = T - ta;
+        if (test < a.min_weight) { done = true; break; }
+        cr = fmaf(ta, g1.z, cr);
+        cg = fmaf(ta, g1.w, cg);
+        cb = fmaf(ta, s2[i], cb);
+        T = test;
+      }
+    }
+    if (__syncthreads_and(done)) break;
+  }
+  if (inside) {
+    float* o = image + ((size_t)py * a.width + px) * 3;
+    o[0] = cr; o[1] = cg; o[2] = cb;
+  }
+}
+
+}  // namespace
+
+int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
+                     FrameGeom geom, const GsbParams& prm, cudaStream_t st) {
+  const int tiles = geom.tiles_x * geom.tiles_y;
+  if (tiles <= 0) return 0;
+  CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max};
+  composite_kernel<GSB_SEM_REF_CPU><<<tiles, 256, 0, st>>>(ranges, payload, rec, nullptr, image, a);
+  return (int)cudaGetLastError();
+}
+
+int launch_composite_cu(const uint2* ranges, const uint32_t* payload, const float4* rec, const float4* bbox,
+                        float* image, FrameGeom geom, const GsbParams& prm, cudaStream_t st) {
+  const int tiles = geom.tiles_x * geom.tiles_y;
+  if (tiles <= 0) return 0;
+  CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max};
+  composite_kernel<GSB_SEM_REF_CU><<<tiles, 256, 0, st>>>(ranges, payload, rec, bbox, image, a);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest of the reference op's own arguments (gsb_render_image; splat/c/render.cu:90-101): rows are
+// already depth-sorted, so the row index is the depth rank and becomes the low key word.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floor_div_i(int a, int b) {
+  int q = a / b;
+  return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+__global__ void __launch_bounds__(256)
+ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restrict__ colors,
+              const float* __restrict__ conic, const float* __restrict__ min_x, const float* __restrict__ max_x,
+              const float* __restrict__ min_y, const float* __restrict__ max_y, const float* __restrict__ opacity,
+              FrameGeom geom, int sem, int T, uint32_t* __restrict__ depth_key, float4* __restrict__ rec,
+              float4* __restrict__ bbox, ushort4* __restrict__ rect, uint32_t* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float kq = -0.72134752044448170368f;
+  const float mx = means[2 * i], my = means[2 * i + 1];
+  const float i00 = conic[4 * i], i01 = conic[4 * i + 1], i10 = conic[4 * i + 2], i11 = conic[4 * i + 3];
+  const float mnx = min_x[i], mxx = max_x[i], mny = min_y[i], mxy = max_y[i];
+  const float op = opacity[i];
+  int tx0, tx1, ty0, ty1;
+  bool nan = !(mnx == mnx) || !(mxx == mxx) || !(mny == mny) || !(mxy == mxy);
+  const float big = 1073741824.0f;
+  if (sem == GSB_SEM_REF_CU) {
+    // render.cu:55-60: pixel p is a candidate iff min <= p <= max (inclusive, per pixel); mean -> int (:8-9)
+    rec[3 * i + 0] = make_float4(truncf(mx), truncf(my), kq * i00, kq * (2.0f * i01));
+    rec[3 * i + 1] = make_float4(kq * i11, op, colors[3 * i], colors[3 * i + 1]);
+    int x0 = (int)ceilf(fminf(fmaxf(mnx, -big), big)), x1 = (int)floorf(fminf(fmaxf(mxx, -big), big));
+    int y0 = (int)ceilf(fminf(fmaxf(mny, -big), big)), y1 = (int)floorf(fminf(fmaxf(mxy, -big), big));
+    x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, geom.width - 1); y1 = min(y1, geom.height - 1);
+    tx0 = x0 / T; tx1 = x1 >= x0 ? x1 / T : -1; ty0 = y0 / T; ty1 = y1 >= y0 ? y1 / T : -1;
+    if (x1 < x0) { tx0 = 0; tx1 = -1; }
+    if (y1 < y0) { ty0 = 0; ty1 = -1; }
+  } else {
+    const float op2 = 1.0f / (1.0f + expf(-op));  // the CPU path applies a second sigmoid (:164)
+    rec[3 * i + 0] = make_float4(mx, my, kq * i00, kq * (i01 + i10));
+    rec[3 * i + 1] = make_float4(kq * i11, op2, colors[3 * i], colors[3 * i + 1]);
+    int imn = (int)fminf(fmaxf(mnx, -big), big), imx = (int)fminf(fmaxf(mxx, -big), big);
+    tx0 = max(floor_div_i(imn - 1, T), 0); tx1 = min(floor_div_i(imx, T), geom.tiles_x - 1);
+    imn = (int)fminf(fmaxf(mny, -big), big); imx = (int)fminf(fmaxf(mxy, -big), big);
+    ty0 = max(floor_div_i(imn - 1, T), 0); ty1 = min(floor_div_i(imx, T), geom.tiles_y - 1);
+  }
+  rec[3 * i + 2] = make_float4(colors[3 * i + 2], 0.f, op, 0.f);
+  bbox[i] = make_float4(mnx, mny, mxx, mxy);
+  uint32_t cnt = 0;
+  if (!nan && tx1 >= tx0 && ty1 >= ty0) cnt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+  rect[i] = cnt ? make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1)
+                : make_ushort4(0, 0, 0, 0);
+  count[i] = cnt;
+  depth_key[i] = (uint32_t)i;
+}
+
+int launch_ingest_preprocessed(int64_t m, const float* means, const float* colors, const float* conic,
+                               const float* min_x, const float* max_x, const float* min_y, const float* max_y,
+                               const float* opacity, FrameGeom geom, const GsbParams& prm, uint32_t* depth_key,
+                               float4* rec, float4* bbox, ushort4* rect, uint32_t* count, cudaStream_t st) {
+  if (m == 0) return 0;
+  ingest_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, means, colors, conic, min_x, max_x, min_y, max_y,
+                                                            opacity, geom, prm.semantics, prm.tile_size, depth_key,
+                                                            rec, bbox, rect, count);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gsb

@@ -1,0 +1,112 @@
+// gsb_internal.cuh -- shared declarations of libgsb_b200.so (sm_100a only).
+//
+// Data layout in HBM (one GsbContext = one device):
+//   scene (gsb_upload):  planar SoA, 14 fp32 planes of length n_pad (n rounded up to 4):
+//                        x y z | sx sy sz | qw qx qy qz | r g b | opacity_logit      (56 B/Gaussian)
+//   per frame (project): depth_key u32[N]  float_as_uint(z_view), 0xFFFFFFFF when culled
+//                        rec float4[3N]    AoS compositing record, 48 B/Gaussian:
+//                                          {mx,my,qa,qb} {qc,op2,r,g} {b, radius, sig_op, 0}
+//                                          qa,qb,qc = conic pre-scaled by -0.5*log2(e)
+//                        rect ushort4[N]   tile rect tx0,tx1,ty0,ty1 (count==0 => unused)
+//                        count u32[N]      tiles touched
+//   binning:             offsets u32[N]    exclusive scan of count (index or depth-rank order)
+//                        keys u64[K] x2, payload u32[K] x2   ping-pong buffers of the radix sort
+//   ranges:              uint2[tiles]      [start,end) into the sorted arrays
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsb.h"
+
+#define GSB_CUDA_TRY(expr)                         \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+#define GSB_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != GSB_OK) return _s; \
+  } while (0)
+
+namespace gsb {
+
+constexpr int kTile = 16;              // pixels per tile edge (the only size the kernels are built for)
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kMaxPasses = 8;
+
+// ---- scene planes ----
+enum Plane { PX = 0, PY, PZ, PSX, PSY, PSZ, PQW, PQX, PQY, PQZ, PR, PG, PB, POP, kNumPlanes };
+
+struct FrameGeom {
+  int width, height;
+  int tiles_x, tiles_y;
+};
+
+// extra per-Gaussian outputs written only by the debug/preprocess variant of the projection kernel
+struct DebugOut {
+  float* cov2d;   // (N,4)
+  float* conic;   // (N,4) unscaled inverse covariance
+  float* bbox;    // (N,4) min_x,min_y,max_x,max_y
+};
+
+// ---- kernel launchers (each returns a cudaError_t as int; all async on `st`) ----
+int launch_repack(const float* xyz, const float* scales, const float* quats, const float* colors,
+                  const float* opacity, float* planes, int64_t n, int64_t n_pad, cudaStream_t st);
+
+int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
+                   FrameGeom geom, uint32_t* depth_key, float4* rec, ushort4* rect, uint32_t* count,
+                   uint32_t* m_counter, const DebugOut* dbg, cudaStream_t st);
+
+// exclusive scan of count[perm ? perm[i] : i] for i < n  -> offsets[i]; total -> *total.
+// `status` needs scan_status_words(n) zeroed u32 words.
+size_t scan_status_words(int64_t n);
+int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* total,
+                uint32_t* status, cudaStream_t st);
+
+int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
+                const uint32_t* depth_key, const ushort4* rect, const uint32_t* count, int tiles_x,
+                uint64_t* keys, uint32_t* payload, cudaStream_t st);
+
+// ---- onesweep radix sort ----
+struct SortPlan {
+  int begin_bit, end_bit, passes;
+  int64_t n;
+  int64_t tiles;          // onesweep tiles per pass
+  size_t control_words;   // u32 words of control memory (histograms + tickets + look-back status)
+};
+template <typename KeyT>
+SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit);
+// Sorts (keys_a, vals_a) using (keys_b, vals_b) as the alternate buffer.  Returns in *result_in_a
+// whether the sorted data ended in the a-buffers (even number of passes).  `control` must hold
+// plan.control_words zeroed u32 words.
+template <typename KeyT>
+int launch_sort(const SortPlan& plan, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
+                uint32_t* control, bool* result_in_a, int* launches, cudaStream_t st);
+
+int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k, uint2* ranges, cudaStream_t st);
+
+int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
+                     FrameGeom geom, const GsbParams& prm, cudaStream_t st);
+
+// egress helpers
+int launch_hwc_to_whc(const float* src_hw3, float* dst_wh3, int width, int height, cudaStream_t st);
+int launch_to_u8(const float* src, uint8_t* dst, int64_t n, cudaStream_t st);
+int launch_gather_preprocess(const uint32_t* order, int64_t m, const float4* rec, const float* planes, int64_t n_pad,
+                             const uint32_t* depth_key, const DebugOut& dbg, float* points_xy, float* colors,
+                             float* cov2d, float* depths, float* conic, float* radius, float* min_x, float* min_y,
+                             float* max_x, float* max_y, float* sig_op, int32_t* src_index, cudaStream_t st);
+int launch_iota(uint32_t* p, int64_t n, cudaStream_t st);
+
+// pre-projected entry (gsb_render_image): build rec/rect/count/depth_key from the reference op's arguments
+int launch_ingest_preprocessed(int64_t m, const float* means, const float* colors, const float* conic,
+                               const float* min_x, const float* max_x, const float* min_y, const float* max_y,
+                               const float* opacity, FrameGeom geom, const GsbParams& prm, uint32_t* depth_key,
+                               float4* rec, float4* bbox, ushort4* rect, uint32_t* count, cudaStream_t st);
+int launch_composite_cu(const uint2* ranges, const uint32_t* payload, const float4* rec, const float4* bbox,
+                        float* image, FrameGeom geom, const GsbParams& prm, cudaStream_t st);
+
+}  // namespace gsb

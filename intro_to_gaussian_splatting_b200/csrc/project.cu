@@ -1,0 +1,280 @@
+// project.cu -- scene repack + the fused projection kernel.            (compile with --fmad=false)
+//
+// Replaces the torch preprocessing of the reference, GaussianScene.preprocess
+// (splat/gaussian_scene.py:70-111) and everything it calls:
+//   in_view_frustum            splat/utils.py:293-310
+//   get_3d_covariance_matrix   splat/gaussians.py:54-69  (+ build_rotation splat/utils.py:132-155)
+//   ndc2Pix                    splat/utils.py:313-317
+//   compute_2d_covariance      splat/utils.py:320-354
+//   compute_inverted_covariance splat/utils.py:368-393
+//   compute_extent_and_radius  splat/utils.py:409-423
+// plus the closed form of the tile masks of render_image (splat/gaussian_scene.py:208-220).
+//
+// Parity contract: depth, pixel centre, radius, bbox, tile rect and tile count must be BIT-EXACT
+// with the reference's fp32 results, because they decide the sort keys.  torch's CPU kernels fuse
+// multiply-add in some products and not in others (probed), so this TU is
+// compiled with --fmad=false and every fused operation is written as __fmaf_rn explicitly; divisions
+// and square roots are the IEEE-rounded intrinsics.
+//
+// Roofline: HBM.  Algorithmic bytes: 56 B read + 64 B written per in-view Gaussian
+// (depth_key 4 + record 48 + rect 8 + count 4).
+#include "gsb_internal.cuh"
+
+namespace gsb {
+
+// ------------------------------------------------------------------------------------------------
+// repack: reference layouts (N,3)/(N,4)/(N,1) -> 14 planes.  One-time per scene.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ xyz, const float* __restrict__ scales,
+                                                     const float* __restrict__ quats, const float* __restrict__ colors,
+                                                     const float* __restrict__ opacity, float* __restrict__ planes,
+                                                     int64_t n, int64_t n_pad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  bool ok = i < n;
+  // padding rows: a Gaussian behind the camera for any view is impossible, so the kernels bound-check n.
+  planes[PX * n_pad + i] = ok ? xyz[3 * i + 0] : 0.f;
+  planes[PY * n_pad + i] = ok ? xyz[3 * i + 1] : 0.f;
+  planes[PZ * n_pad + i] = ok ? xyz[3 * i + 2] : 0.f;
+  planes[PSX * n_pad + i] = ok ? scales[3 * i + 0] : 0.f;
+  planes[PSY * n_pad + i] = ok ? scales[3 * i + 1] : 0.f;
+  planes[PSZ * n_pad + i] = ok ? scales[3 * i + 2] : 0.f;
+  planes[PQW * n_pad + i] = ok ? quats[4 * i + 0] : 1.f;
+  planes[PQX * n_pad + i] = ok ? quats[4 * i + 1] : 0.f;
+  planes[PQY * n_pad + i] = ok ? quats[4 * i + 2] : 0.f;
+  planes[PQZ * n_pad + i] = ok ? quats[4 * i + 3] : 0.f;
+  planes[PR * n_pad + i] = ok ? colors[3 * i + 0] : 0.f;
+  planes[PG * n_pad + i] = ok ? colors[3 * i + 1] : 0.f;
+  planes[PB * n_pad + i] = ok ? colors[3 * i + 2] : 0.f;
+  planes[POP * n_pad + i] = ok ? opacity[i] : 0.f;
+}
+
+int launch_repack(const float* xyz, const float* scales, const float* quats, const float* colors,
+                  const float* opacity, float* planes, int64_t n, int64_t n_pad, cudaStream_t st) {
+  if (n_pad == 0) return 0;
+  unsigned blocks = (unsigned)((n_pad + 255) / 256);
+  repack_kernel<<<blocks, 256, 0, st>>>(xyz, scales, quats, colors, opacity, planes, n, n_pad);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection
+// ------------------------------------------------------------------------------------------------
+struct ProjectArgs {
+  GsbCamera cam;
+  float minimum_z, fov_clamp, det_min, lambda_floor, sigma_extent;
+  int tile_size, tiles_x, tiles_y;
+};
+
+// [x y z 1] @ M[:, j] as torch's (N,4)@(4,4) evaluates it: one rounded product, then an FMA chain.
+__device__ __forceinline__ float rowvec_col(float x, float y, float z, const float* M, int j) {
+  float t = __fmul_rn(x, M[0 * 4 + j]);
+  t = __fmaf_rn(y, M[1 * 4 + j], t);
+  t = __fmaf_rn(z, M[2 * 4 + j], t);
+  t = __fmaf_rn(1.0f, M[3 * 4 + j], t);
+  return t;
+}
+
+__device__ __forceinline__ float dot3_unfused(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
+
+__device__ __forceinline__ float dot3_fmachain(float a0, float b0, float a1, float b1, float a2, float b2) {
+  float t = __fmul_rn(a0, b0);
+  t = __fmaf_rn(a1, b1, t);
+  return __fmaf_rn(a2, b2, t);
+}
+
+__device__ __forceinline__ float clamp_torch(float v, float lo, float hi) {
+  if (v != v) return v;
+  float t = v < lo ? lo : v;
+  return t > hi ? hi : t;
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+  int q = a / b;
+  return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+// Closed form of the reference tile mask along one axis (splat/gaussian_scene.py:209-217):
+//   tile t (t_min = t*T) is hit  iff  mn <= t_min + T  and  mx >= t_min.
+// mn, mx are integer-valued floats (floor/ceil results) or non-finite.
+__device__ __forceinline__ void tile_interval(float mn, float mx, int T, int ntiles, int& lo, int& hi) {
+  if (!(mn == mn) || !(mx == mx)) { lo = 0; hi = -1; return; }  // NaN never passes a comparison
+  const float big = 1073741824.0f;                               // 2^30, exact; keeps the int math in range
+  int imn = (int)fminf(fmaxf(mn, -big), big);
+  int imx = (int)fminf(fmaxf(mx, -big), big);
+  int l = floor_div(imn - T + (T - 1), T);  // ceil((mn - T)/T)
+  int h = floor_div(imx, T);                // floor(mx/T)
+  lo = l < 0 ? 0 : l;
+  hi = h > ntiles - 1 ? ntiles - 1 : h;
+}
+
+template <bool kDebug>
+__global__ void __launch_bounds__(256)
+project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const __grid_constant__ ProjectArgs a,
+               uint32_t* __restrict__ depth_key, float4* __restrict__ rec, ushort4* __restrict__ rect,
+               uint32_t* __restrict__ count, uint32_t* __restrict__ m_counter, DebugOut dbg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (i < n) {
+    const float x = planes[PX * n_pad + i], y = planes[PY * n_pad + i], z = planes[PZ * n_pad + i];
+    const float* V = a.cam.world2view;
+    const float* F = a.cam.full_proj;
+    const float vz = rowvec_col(x, y, z, V, 2);
+    keep = vz >= a.minimum_z;  // in_view_frustum; the ONLY cull (no x/y frustum test in the reference)
+    uint32_t cnt = 0;
+    if (keep) {
+      // issue the remaining loads early so they overlap the arithmetic below
+      const float sx = planes[PSX * n_pad + i], sy = planes[PSY * n_pad + i], sz = planes[PSZ * n_pad + i];
+      float q0 = planes[PQW * n_pad + i], q1 = planes[PQX * n_pad + i], q2 = planes[PQY * n_pad + i],
+            q3 = planes[PQZ * n_pad + i];
+      const float cr = planes[PR * n_pad + i], cg = planes[PG * n_pad + i], cb = planes[PB * n_pad + i];
+      const float logit = planes[POP * n_pad + i];
+
+      const float vx = rowvec_col(x, y, z, V, 0);
+      const float vy = rowvec_col(x, y, z, V, 1);
+      // pixel centre: clip space -> NDC -> ndc2Pix (principal point is not used on this path)
+      const float cx = rowvec_col(x, y, z, F, 0);
+      const float cy = rowvec_col(x, y, z, F, 1);
+      const float cw = rowvec_col(x, y, z, F, 3);
+      const float ndx = __fdiv_rn(cx, cw), ndy = __fdiv_rn(cy, cw);
+      const float Wf = (float)a.cam.width, Hf = (float)a.cam.height;
+      const float px = __fmul_rn(__fmul_rn(__fadd_rn(ndx, 1.0f), __fsub_rn(Wf, 1.0f)), 0.5f);
+      const float py = __fmul_rn(__fmul_rn(__fadd_rn(ndy, 1.0f), __fsub_rn(Hf, 1.0f)), 0.5f);
+
+      // ---- 3-D covariance: F.normalize, then build_rotation normalises again ----
+      float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), __fmul_rn(q2, q2)),
+                                       __fmul_rn(q3, q3)));
+      float dn = nrm > 1e-12f ? nrm : 1e-12f;
+      q0 = __fdiv_rn(q0, dn); q1 = __fdiv_rn(q1, dn); q2 = __fdiv_rn(q2, dn); q3 = __fdiv_rn(q3, dn);
+      float n2 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), __fmul_rn(q2, q2)),
+                                      __fmul_rn(q3, q3)));
+      const float r = __fdiv_rn(q0, n2), qx = __fdiv_rn(q1, n2), qy = __fdiv_rn(q2, n2), qz = __fdiv_rn(q3, n2);
+      float R[9];
+      R[0] = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(qy, qy), __fmul_rn(qz, qz))));
+      R[1] = __fmul_rn(2.0f, __fsub_rn(__fmul_rn(qx, qy), __fmul_rn(r, qz)));
+      R[2] = __fmul_rn(2.0f, __fadd_rn(__fmul_rn(qx, qz), __fmul_rn(r, qy)));
+      R[3] = __fmul_rn(2.0f, __fadd_rn(__fmul_rn(qx, qy), __fmul_rn(r, qz)));
+      R[4] = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qz, qz))));
+      R[5] = __fmul_rn(2.0f, __fsub_rn(__fmul_rn(qy, qz), __fmul_rn(r, qx)));
+      R[6] = __fmul_rn(2.0f, __fsub_rn(__fmul_rn(qx, qz), __fmul_rn(r, qy)));
+      R[7] = __fmul_rn(2.0f, __fadd_rn(__fmul_rn(qy, qz), __fmul_rn(r, qx)));
+      R[8] = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy))));
+      const float s[3] = {sx, sy, sz};
+      float Ms[9];
+#pragma unroll
+      for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) Ms[ii * 3 + jj] = __fmul_rn(R[ii * 3 + jj], s[jj]);  // R @ diag(s)
+      float S3[9];
+#pragma unroll
+      for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)  // M @ M^T, batched bmm: unfused
+          S3[ii * 3 + jj] = dot3_unfused(Ms[ii * 3 + 0], Ms[jj * 3 + 0], Ms[ii * 3 + 1], Ms[jj * 3 + 1], Ms[ii * 3 + 2],
+                                         Ms[jj * 3 + 2]);
+
+      // ---- EWA 2-D covariance ----
+      const float limx = __fmul_rn(a.fov_clamp, a.cam.tan_fovx);
+      const float limy = __fmul_rn(a.fov_clamp, a.cam.tan_fovy);
+      const float tx = __fmul_rn(clamp_torch(__fdiv_rn(vx, vz), -limx, limx), vz);
+      const float ty = __fmul_rn(clamp_torch(__fdiv_rn(vy, vz), -limy, limy), vz);
+      const float z2 = __fmul_rn(vz, vz);
+      float J[6];  // rows 0,1 of J (row 2 is zero and only feeds discarded outputs)
+      J[0] = __fdiv_rn(a.cam.f_x, vz); J[1] = 0.f; J[2] = __fdiv_rn(-__fmul_rn(a.cam.f_x, tx), z2);
+      J[3] = 0.f; J[4] = __fdiv_rn(a.cam.f_y, vz); J[5] = __fdiv_rn(-__fmul_rn(a.cam.f_y, ty), z2);
+      // W = world2view[:3,:3].T  =>  W[l][k] = V[k][l];  (W.T)[l][k] = V[l][k]
+      float T1[6], T2[6], T3[6];
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)  // J @ W (broadcast 3x3): FMA chain
+          T1[ii * 3 + k] = dot3_fmachain(J[ii * 3 + 0], V[k * 4 + 0], J[ii * 3 + 1], V[k * 4 + 1], J[ii * 3 + 2], V[k * 4 + 2]);
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)  // @ Sigma (batched): unfused
+          T2[ii * 3 + k] = dot3_unfused(T1[ii * 3 + 0], S3[0 * 3 + k], T1[ii * 3 + 1], S3[1 * 3 + k], T1[ii * 3 + 2], S3[2 * 3 + k]);
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)  // @ W.T (broadcast): FMA chain
+          T3[ii * 3 + k] = dot3_fmachain(T2[ii * 3 + 0], V[0 * 4 + k], T2[ii * 3 + 1], V[1 * 4 + k], T2[ii * 3 + 2], V[2 * 4 + k]);
+      float c2[4];
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)  // @ J^T (batched): unfused
+          c2[ii * 2 + jj] = dot3_unfused(T3[ii * 3 + 0], J[jj * 3 + 0], T3[ii * 3 + 1], J[jj * 3 + 1], T3[ii * 3 + 2], J[jj * 3 + 2]);
+      const float ca = c2[0], cbb = c2[1], cc = c2[2], cd = c2[3];
+
+      // ---- conic (det clamp 1e-3), radius (lambda floor 0.1, 3 sigma), bbox ----
+      float det = __fsub_rn(__fmul_rn(ca, cd), __fmul_rn(cbb, cc));
+      det = (det != det) ? det : (det < a.det_min ? a.det_min : det);
+      const float i00 = __fdiv_rn(cd, det), i11 = __fdiv_rn(ca, det);
+      const float i01 = __fdiv_rn(-cbb, det), i10 = __fdiv_rn(-cc, det);
+      const float mid = __fmul_rn(0.5f, __fadd_rn(ca, cd));
+      const float det2 = __fsub_rn(__fmul_rn(ca, cd), __fmul_rn(cbb, cbb));
+      const float im = __fsub_rn(__fmul_rn(mid, mid), det2);
+      const float mv = (im != im) ? im : (im > a.lambda_floor ? im : a.lambda_floor);
+      const float sq = __fsqrt_rn(mv);
+      const float l1 = __fadd_rn(mid, sq), l2 = __fsub_rn(mid, sq);
+      const float lm = (l1 != l1 || l2 != l2) ? __int_as_float(0x7fc00000) : (l1 > l2 ? l1 : l2);
+      const float rad = ceilf(__fmul_rn(a.sigma_extent, __fsqrt_rn(lm)));
+      const float mnx = floorf(__fsub_rn(px, rad)), mny = floorf(__fsub_rn(py, rad));
+      const float mxx = ceilf(__fadd_rn(px, rad)), mxy = ceilf(__fadd_rn(py, rad));
+
+      int tx0, tx1, ty0, ty1;
+      tile_interval(mnx, mxx, a.tile_size, a.tiles_x, tx0, tx1);
+      tile_interval(mny, mxy, a.tile_size, a.tiles_y, ty0, ty1);
+      if (tx1 >= tx0 && ty1 >= ty0) cnt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+
+      // opacity as the CPU path uses it: sigmoid(sigmoid(logit)) (splat/gaussian_scene.py:143 then :164)
+      const float sig1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
+      const float op2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sig1)));
+      const float kq = -0.72134752044448170368f;  // -0.5 * log2(e): exp(-q/2) = exp2(kq*q)
+      rec[3 * i + 0] = make_float4(px, py, __fmul_rn(kq, i00), __fmul_rn(kq, __fadd_rn(i01, i10)));
+      rec[3 * i + 1] = make_float4(__fmul_rn(kq, i11), op2, cr, cg);
+      rec[3 * i + 2] = make_float4(cb, rad, sig1, 0.f);
+      rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
+      depth_key[i] = __float_as_uint(vz);
+      if (kDebug) {
+        reinterpret_cast<float4*>(dbg.cov2d)[i] = make_float4(ca, cbb, cc, cd);
+        reinterpret_cast<float4*>(dbg.conic)[i] = make_float4(i00, i01, i10, i11);
+        reinterpret_cast<float4*>(dbg.bbox)[i] = make_float4(mnx, mny, mxx, mxy);
+      }
+    } else {
+      depth_key[i] = 0xFFFFFFFFu;  // sorts behind every real depth (z >= 0.2 > 0, finite)
+      rect[i] = make_ushort4(0, 0, 0, 0);
+    }
+    count[i] = cnt;
+  }
+  // M = number of in-view Gaussians: one atomic per block
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned b = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_cnt, __popc(b));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(m_counter, (uint32_t)s_cnt);
+}
+
+int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
+                   FrameGeom geom, uint32_t* depth_key, float4* rec, ushort4* rect, uint32_t* count,
+                   uint32_t* m_counter, const DebugOut* dbg, cudaStream_t st) {
+  if (n == 0) return 0;
+  ProjectArgs a;
+  a.cam = cam;
+  a.minimum_z = prm.minimum_z; a.fov_clamp = prm.fov_clamp; a.det_min = prm.det_min;
+  a.lambda_floor = prm.lambda_floor; a.sigma_extent = prm.sigma_extent;
+  a.tile_size = prm.tile_size; a.tiles_x = geom.tiles_x; a.tiles_y = geom.tiles_y;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dbg)
+    project_kernel<true><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, *dbg);
+  else
+    project_kernel<false><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, DebugOut{});
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gsb
