@@ -1,0 +1,669 @@
+// gsb_api.cu -- the C ABI (include/gsb.h): context, scratch management, kernel-chain orchestration.
+//
+// Frame pipeline (one stream, no CPU work between kernels except ONE read-back of the tile-instance
+// count K, needed to size the key buffers and the sort grid):
+//
+//   FULL :  project -> scan(index order) -> [K] -> emit -> histogram + p x onesweep(K, 64-bit keys)
+//           -> ranges -> composite                          p = ceil((32 + tile_bits) / 8)
+//   SPLIT:  project -> histogram + 4 x onesweep(N, 32-bit depth keys) -> scan(depth order) -> [K]
+//           -> emit(depth order) -> histogram + ceil(tile_bits/8) x onesweep(K, tile digits only)
+//           -> ranges -> composite
+//
+// Both leave bit-identical sorted (key, payload) arrays: an LSD radix sort orders by the low (depth)
+// digits first, and every tile instance of a Gaussian shares those digits, so they can be sorted once
+// per Gaussian BEFORE the expansion instead of once per instance after it.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gsb_internal.cuh"
+
+using namespace gsb;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return GSB_OK;
+    size_t want = bytes + bytes / 4 + 256;  // geometric growth
+    if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return (int)e; }
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return GSB_E_ALLOC; }
+    cap = want;
+    return GSB_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int tile_grid_dim(int extent, int T, int full_cover) {
+  if (full_cover) return (extent + T - 1) / T;
+  int span = extent - T;  // len(range(0, extent - T, T)): splat/gaussian_scene.py:208,:214
+  return span <= 0 ? 0 : (span + T - 1) / T;
+}
+
+int ceil_log2(int64_t v) {
+  int b = 0;
+  while (((int64_t)1 << b) < v) ++b;
+  return b < 1 ? 1 : b;
+}
+
+constexpr int kCtlHeaderWords = 16;  // [0] = M counter, [1] = K total
+
+}  // namespace
+
+struct GsbContext {
+  int device = 0;
+  int64_t n = 0, n_pad = 0;
+  DevBuf planes, staging;
+  // per-Gaussian frame data
+  DevBuf depth_key, rec, rect, count, offsets, bbox;
+  DevBuf dbg_cov2d, dbg_conic, dbg_bbox;
+  DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b;
+  // per-instance
+  DevBuf keys_a, keys_b, vals_a, vals_b;
+  DevBuf ranges, control, control2;
+  DevBuf image, image2, scratch;
+  uint32_t* pinned = nullptr;  // [0]=M, [1]=K
+  // state of the last frame
+  bool have_frame = false;
+  bool sorted_in_a = true;
+  bool emitted_valid = false;
+  bool order_in_a = true;
+  bool have_order = false;
+  int64_t frame_rows = 0;  // rows of the per-Gaussian arrays of the last frame (N, or M for gsb_render_image)
+  GsbFrameInfo info{};
+  cudaEvent_t ev[GSB_NUM_STAGES + 1]{};
+  bool ev_valid[GSB_NUM_STAGES + 1]{};
+  float stage_ms[GSB_NUM_STAGES]{};
+  bool have_times = false;
+};
+
+namespace {
+
+struct StageTimer {
+  GsbContext* c;
+  cudaStream_t st;
+  bool on;
+  void mark(int idx) {
+    if (!on) return;
+    cudaEventRecord(c->ev[idx], st);
+    c->ev_valid[idx] = true;
+  }
+};
+
+int check_params(const GsbCamera* cam, const GsbParams* prm) {
+  if (!cam || !prm) return GSB_E_INVALID_ARG;
+  if (prm->tile_size != kTile) return GSB_E_UNSUPPORTED;
+  if (cam->width <= 0 || cam->height <= 0) return GSB_E_INVALID_ARG;
+  if (cam->width > 65535 * kTile || cam->height > 65535 * kTile) return GSB_E_UNSUPPORTED;
+  if (prm->semantics != GSB_SEM_REF_CPU && prm->semantics != GSB_SEM_REF_CU) return GSB_E_INVALID_ARG;
+  if (prm->sort_mode < GSB_SORT_AUTO || prm->sort_mode > GSB_SORT_SPLIT) return GSB_E_INVALID_ARG;
+  return GSB_OK;
+}
+
+// depth sort of the per-Gaussian keys (N items): leaves the order in ord_vals_{a|b}
+int depth_sort(GsbContext* c, int64_t n, uint32_t* control_words, cudaStream_t st, int* launches, int* passes) {
+  GSB_TRY(c->ord_keys_a.ensure((size_t)n * 4));
+  GSB_TRY(c->ord_keys_b.ensure((size_t)n * 4));
+  GSB_TRY(c->ord_vals_a.ensure((size_t)n * 4));
+  GSB_TRY(c->ord_vals_b.ensure((size_t)n * 4));
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->ord_keys_a.p, c->depth_key.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  GSB_CUDA_TRY((cudaError_t)launch_iota(c->ord_vals_a.as<uint32_t>(), n, st));
+  ++*launches;
+  SortPlan plan = make_sort_plan<uint32_t>(n, 0, 32);
+  bool in_a = true;
+  GSB_CUDA_TRY((cudaError_t)launch_sort<uint32_t>(plan, c->ord_keys_a.as<uint32_t>(), c->ord_vals_a.as<uint32_t>(),
+                                                  c->ord_keys_b.as<uint32_t>(), c->ord_vals_b.as<uint32_t>(),
+                                                  control_words, &in_a, launches, st));
+  c->order_in_a = in_a;
+  c->have_order = true;
+  *passes = plan.passes;
+  return GSB_OK;
+}
+
+// everything after the per-Gaussian records exist: scan -> K -> emit -> sort -> ranges.
+// `n_rows` per-Gaussian rows; `perm` optional emission order; `low_bits_sorted`: emission order already
+// sorts the low key word (SPLIT mode / pre-sorted rows), so only the tile digits need radix passes.
+int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, FrameGeom geom,
+                 uint32_t* ctl_header, uint32_t* scan_status, cudaStream_t st, StageTimer& tm, int* launches) {
+  GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
+  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl_header + 1,
+                                        scan_status, st));
+  ++*launches;
+  tm.mark(GSB_STAGE_SCAN + 1);
+  // the one host round trip of the frame: M and K
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl_header, 8, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  const int64_t m = c->pinned[0], k = c->pinned[1];
+  if (k >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;  // look-back words carry 30-bit counts
+  c->info.m_in_view = m;
+  c->info.k_instances = k;
+
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->ranges.p, 0, (size_t)(tiles > 0 ? tiles : 1) * 8, st));
+  GSB_TRY(c->keys_a.ensure((size_t)k * 8 + 8));
+  GSB_TRY(c->keys_b.ensure((size_t)k * 8 + 8));
+  GSB_TRY(c->vals_a.ensure((size_t)k * 4 + 4));
+  GSB_TRY(c->vals_b.ensure((size_t)k * 4 + 4));
+
+  const int tile_bits = ceil_log2(tiles);
+  SortPlan plan = low_bits_sorted ? make_sort_plan<uint64_t>(k, 32, 32 + tile_bits)
+                                  : make_sort_plan<uint64_t>(k, 0, 32 + tile_bits);
+  GSB_TRY(c->control2.ensure(plan.control_words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+
+  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl_header + 1, n_rows, c->depth_key.as<uint32_t>(),
+                                        c->rect.as<ushort4>(), c->count.as<uint32_t>(), geom.tiles_x,
+                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
+  ++*launches;
+  tm.mark(GSB_STAGE_EMIT + 1);
+  bool in_a = true;
+  GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
+                                                  c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(),
+                                                  c->control2.as<uint32_t>(), &in_a, launches, st));
+  c->sorted_in_a = in_a;
+  c->emitted_valid = (plan.passes == 1);  // with one pass the a-buffers still hold the emitted order
+  c->info.sort_passes = (k > 0) ? plan.passes : 0;
+  tm.mark(GSB_STAGE_SORT + 1);
+  const uint64_t* sk = in_a ? c->keys_a.as<uint64_t>() : c->keys_b.as<uint64_t>();
+  GSB_CUDA_TRY((cudaError_t)launch_ranges(sk, ctl_header + 1, k, c->ranges.as<uint2>(), st));
+  if (k > 0) ++*launches;
+  tm.mark(GSB_STAGE_RANGES + 1);
+  return GSB_OK;
+}
+
+void finish_times(GsbContext* c, cudaStream_t st, bool on) {
+  c->have_times = false;
+  if (!on) return;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return;
+  for (int s = 0; s < GSB_NUM_STAGES; ++s) {
+    c->stage_ms[s] = 0.f;
+    if (!c->ev_valid[s + 1]) continue;
+    int prev = s;  // nearest earlier recorded mark
+    while (prev > 0 && !c->ev_valid[prev]) --prev;
+    float ms = 0.f;
+    if (c->ev_valid[prev] && cudaEventElapsedTime(&ms, c->ev[prev], c->ev[s + 1]) == cudaSuccess) c->stage_ms[s] = ms;
+  }
+  c->have_times = true;
+}
+
+// projection + binning + sort + compositing into a DEVICE image buffer
+int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float* dev_image, cudaStream_t st) {
+  GSB_TRY(check_params(cam, prm));
+  if (c->n_pad == 0 && c->n != 0) return GSB_E_NO_SCENE;
+  if (!c->planes.p && c->n > 0) return GSB_E_NO_SCENE;
+  if (prm->semantics != GSB_SEM_REF_CPU) return GSB_E_UNSUPPORTED;  // REF_CU is served by gsb_render_image
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
+                 tile_grid_dim(cam->height, kTile, prm->full_cover)};
+  const bool split = prm->sort_mode != GSB_SORT_FULL;  // AUTO = SPLIT
+  int launches = 0;
+  c->have_frame = false;
+  c->have_order = false;
+  std::memset(&c->info, 0, sizeof(c->info));
+  c->info.n = n; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
+  for (bool& v : c->ev_valid) v = false;
+  StageTimer tm{c, st, prm->collect_stage_times != 0};
+
+  const size_t rows = (size_t)(n > 0 ? n : 1);
+  GSB_TRY(c->depth_key.ensure(rows * 4));
+  GSB_TRY(c->rec.ensure(rows * 48));
+  GSB_TRY(c->rect.ensure(rows * 8));
+  GSB_TRY(c->count.ensure(rows * 4));
+  SortPlan dplan = make_sort_plan<uint32_t>(n, 0, 32);
+  const size_t scan_words = scan_status_words(n);
+  const size_t ctl_words = kCtlHeaderWords + scan_words + (split ? dplan.control_words : 0);
+  GSB_TRY(c->control.ensure(ctl_words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, ctl_words * 4, st));
+  uint32_t* hdr = c->control.as<uint32_t>();
+  uint32_t* scan_status = hdr + kCtlHeaderWords;
+  uint32_t* dsort_ctl = scan_status + scan_words;
+
+  tm.mark(0);
+  GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, *cam, *prm, geom, c->depth_key.as<uint32_t>(),
+                                           c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), hdr,
+                                           nullptr, st));
+  if (n > 0) ++launches;
+  tm.mark(GSB_STAGE_PROJECT + 1);
+  const uint32_t* perm = nullptr;
+  if (split && n > 0) {
+    int dp = 0;
+    GSB_TRY(depth_sort(c, n, dsort_ctl, st, &launches, &dp));
+    c->info.depth_passes = dp;
+    perm = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
+    tm.mark(GSB_STAGE_DEPTH_SORT + 1);
+  }
+  GSB_TRY(bin_and_sort(c, n, perm, split, geom, hdr, scan_status, st, tm, &launches));
+
+  if (!prm->full_cover)  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
+    GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
+  const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
+  GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, *prm, st));
+  if (geom.tiles_x * geom.tiles_y > 0) ++launches;
+  tm.mark(GSB_STAGE_COMPOSITE + 1);
+  c->info.kernel_launches = launches;
+  c->frame_rows = n;
+  c->have_frame = true;
+  finish_times(c, st, tm.on);
+  return GSB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int gsb_version(void) { return GSB_API_VERSION; }
+
+const char* gsb_error_string(int s) {
+  switch (s) {
+    case GSB_OK: return "ok";
+    case GSB_E_INVALID_ARG: return "invalid argument";
+    case GSB_E_NO_SCENE: return "no Gaussians uploaded (call gsb_upload first)";
+    case GSB_E_NO_FRAME: return "no frame rendered yet";
+    case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; K < 2^30)";
+    case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case GSB_E_ALLOC: return "device memory allocation failed";
+    default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown error";
+  }
+}
+
+void gsb_default_params(GsbParams* p) {
+  if (!p) return;
+  p->tile_size = 16;
+  p->minimum_z = 0.2f;
+  p->fov_clamp = 1.3f;
+  p->det_min = 1e-3f;
+  p->lambda_floor = 0.1f;
+  p->sigma_extent = 3.0f;
+  p->min_weight = 1e-6f;
+  p->alpha_max = 0.99f;
+  p->semantics = GSB_SEM_REF_CPU;
+  p->full_cover = 0;
+  p->sort_mode = GSB_SORT_AUTO;
+  p->collect_stage_times = 0;
+}
+
+int gsb_create(GsbContext** out, int device) {
+  if (!out) return GSB_E_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return GSB_E_NO_DEVICE; }
+  if (device < 0 || device >= count) return GSB_E_INVALID_ARG;
+  GSB_CUDA_TRY(cudaSetDevice(device));
+  GsbContext* c = new (std::nothrow) GsbContext();
+  if (!c) return GSB_E_ALLOC;
+  c->device = device;
+  if (cudaMallocHost((void**)&c->pinned, 64) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
+  for (auto& e : c->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }
+  *out = c;
+  return GSB_OK;
+}
+
+void gsb_destroy(GsbContext* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->offsets, &c->bbox,
+                    &c->dbg_cov2d, &c->dbg_conic, &c->dbg_bbox, &c->ord_keys_a, &c->ord_keys_b, &c->ord_vals_a,
+                    &c->ord_vals_b, &c->keys_a, &c->keys_b, &c->vals_a, &c->vals_b, &c->ranges, &c->control,
+                    &c->control2, &c->image, &c->image2, &c->scratch};
+  for (DevBuf* b : bufs) b->release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  delete c;
+}
+
+int gsb_upload(GsbContext* c, int64_t n, const float* xyz, const float* scales, const float* quats,
+               const float* colors, const float* opacity_logit, void* stream) {
+  if (!c || n < 0) return GSB_E_INVALID_ARG;
+  if (n > 0 && (!xyz || !scales || !quats || !colors || !opacity_logit)) return GSB_E_INVALID_ARG;
+  if (n >= ((int64_t)1 << 31)) return GSB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  c->have_frame = false;
+  c->n = n;
+  c->n_pad = (n + 3) & ~(int64_t)3;
+  if (n == 0) return GSB_OK;
+  GSB_TRY(c->planes.ensure((size_t)c->n_pad * kNumPlanes * sizeof(float)));
+  const float* src[5] = {xyz, scales, quats, colors, opacity_logit};
+  const int width[5] = {3, 3, 4, 3, 1};
+  const float* dev[5];
+  size_t need = 0;
+  for (int i = 0; i < 5; ++i)
+    if (!is_device_pointer(src[i])) need += (size_t)n * width[i] * sizeof(float);
+  if (need) GSB_TRY(c->staging.ensure(need));
+  size_t off = 0;
+  for (int i = 0; i < 5; ++i) {
+    if (is_device_pointer(src[i])) { dev[i] = src[i]; continue; }
+    float* d = reinterpret_cast<float*>(c->staging.as<char>() + off);
+    size_t bytes = (size_t)n * width[i] * sizeof(float);
+    GSB_CUDA_TRY(cudaMemcpyAsync(d, src[i], bytes, cudaMemcpyHostToDevice, st));
+    dev[i] = d;
+    off += bytes;
+  }
+  GSB_CUDA_TRY((cudaError_t)launch_repack(dev[0], dev[1], dev[2], dev[3], dev[4], c->planes.as<float>(), n, c->n_pad, st));
+  if (need) {  // host sources may be reused by the caller; staging is ours, so just make the copy complete
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return GSB_OK;
+}
+
+int gsb_render(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float* out_image, void* stream) {
+  if (!c || !out_image) return GSB_E_INVALID_ARG;
+  GSB_TRY(check_params(cam, prm));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (is_device_pointer(out_image)) return render_device(c, cam, prm, out_image, st);
+  const size_t bytes = (size_t)cam->width * cam->height * 3 * sizeof(float);
+  GSB_TRY(c->image.ensure(bytes));
+  GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(out_image, c->image.p, bytes, cudaMemcpyDeviceToHost, st));
+  return GSB_OK;
+}
+
+int gsb_render_wh(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float* out_wh, void* stream) {
+  if (!c || !out_wh) return GSB_E_INVALID_ARG;
+  GSB_TRY(check_params(cam, prm));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)cam->width * cam->height * 3 * sizeof(float);
+  GSB_TRY(c->image.ensure(bytes));
+  GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
+  if (is_device_pointer(out_wh)) {
+    GSB_CUDA_TRY((cudaError_t)launch_hwc_to_whc(c->image.as<float>(), out_wh, cam->width, cam->height, st));
+    return GSB_OK;
+  }
+  GSB_TRY(c->image2.ensure(bytes));
+  GSB_CUDA_TRY((cudaError_t)launch_hwc_to_whc(c->image.as<float>(), c->image2.as<float>(), cam->width, cam->height, st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(out_wh, c->image2.p, bytes, cudaMemcpyDeviceToHost, st));
+  return GSB_OK;
+}
+
+int gsb_render_u8(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, uint8_t* out, void* stream) {
+  if (!c || !out) return GSB_E_INVALID_ARG;
+  GSB_TRY(check_params(cam, prm));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t elems = (int64_t)cam->width * cam->height * 3;
+  GSB_TRY(c->image.ensure((size_t)elems * sizeof(float)));
+  GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
+  if (is_device_pointer(out)) return launch_to_u8(c->image.as<float>(), out, elems, st);
+  GSB_TRY(c->image2.ensure((size_t)elems));
+  GSB_CUDA_TRY((cudaError_t)launch_to_u8(c->image.as<float>(), c->image2.as<uint8_t>(), elems, st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(out, c->image2.p, (size_t)elems, cudaMemcpyDeviceToHost, st));
+  return GSB_OK;
+}
+
+int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, int64_t* m_out, float* points_xy,
+                   float* colors, float* covariance_2d, float* depths, float* inverse_covariance_2d, float* radius,
+                   float* min_x, float* min_y, float* max_x, float* max_y, float* sigmoid_opacity,
+                   int32_t* source_index, void* stream) {
+  if (!c) return GSB_E_INVALID_ARG;
+  GSB_TRY(check_params(cam, prm));
+  if (!c->planes.p && c->n > 0) return GSB_E_NO_SCENE;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  c->have_frame = false;
+  if (m_out) *m_out = 0;
+  if (n == 0) return GSB_OK;
+  FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
+                 tile_grid_dim(cam->height, kTile, prm->full_cover)};
+  GSB_TRY(c->depth_key.ensure((size_t)n * 4));
+  GSB_TRY(c->rec.ensure((size_t)n * 48));
+  GSB_TRY(c->rect.ensure((size_t)n * 8));
+  GSB_TRY(c->count.ensure((size_t)n * 4));
+  GSB_TRY(c->dbg_cov2d.ensure((size_t)n * 16));
+  GSB_TRY(c->dbg_conic.ensure((size_t)n * 16));
+  GSB_TRY(c->dbg_bbox.ensure((size_t)n * 16));
+  SortPlan dplan = make_sort_plan<uint32_t>(n, 0, 32);
+  const size_t ctl_words = kCtlHeaderWords + dplan.control_words;
+  GSB_TRY(c->control.ensure(ctl_words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, ctl_words * 4, st));
+  uint32_t* hdr = c->control.as<uint32_t>();
+  DebugOut dbg{c->dbg_cov2d.as<float>(), c->dbg_conic.as<float>(), c->dbg_bbox.as<float>()};
+  GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, *cam, *prm, geom, c->depth_key.as<uint32_t>(),
+                                           c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), hdr, &dbg, st));
+  int launches = 1, dp = 0;
+  GSB_TRY(depth_sort(c, n, hdr + kCtlHeaderWords, st, &launches, &dp));
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, hdr, 4, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  const int64_t m = c->pinned[0];
+  if (m_out) *m_out = m;
+  if (m == 0) return GSB_OK;
+  // gather into one staging block, then copy each requested field out (device or host destination)
+  const size_t words_per_row = 2 + 3 + 4 + 1 + 4 + 1 + 4 + 1 + 1;
+  GSB_TRY(c->scratch.ensure((size_t)m * words_per_row * 4));
+  float* base = c->scratch.as<float>();
+  float* s_xy = base;            float* s_col = s_xy + 2 * m;   float* s_cov = s_col + 3 * m;
+  float* s_dep = s_cov + 4 * m;  float* s_con = s_dep + m;      float* s_rad = s_con + 4 * m;
+  float* s_mnx = s_rad + m;      float* s_mny = s_mnx + m;      float* s_mxx = s_mny + m;
+  float* s_mxy = s_mxx + m;      float* s_sig = s_mxy + m;      int32_t* s_idx = reinterpret_cast<int32_t*>(s_sig + m);
+  const uint32_t* order = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
+  GSB_CUDA_TRY((cudaError_t)launch_gather_preprocess(order, m, c->rec.as<float4>(), c->planes.as<float>(), c->n_pad,
+                                                     c->depth_key.as<uint32_t>(), dbg, s_xy, s_col, s_cov, s_dep, s_con,
+                                                     s_rad, s_mnx, s_mny, s_mxx, s_mxy, s_sig, s_idx, st));
+  struct { void* dst; const void* src; size_t words; } cp[] = {
+      {points_xy, s_xy, 2}, {colors, s_col, 3}, {covariance_2d, s_cov, 4}, {depths, s_dep, 1},
+      {inverse_covariance_2d, s_con, 4}, {radius, s_rad, 1}, {min_x, s_mnx, 1}, {min_y, s_mny, 1},
+      {max_x, s_mxx, 1}, {max_y, s_mxy, 1}, {sigmoid_opacity, s_sig, 1}, {source_index, s_idx, 1}};
+  for (auto& e : cp)
+    if (e.dst) GSB_CUDA_TRY(cudaMemcpyAsync(e.dst, e.src, (size_t)m * e.words * 4, cudaMemcpyDefault, st));
+  GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  return GSB_OK;
+}
+
+int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int64_t m, const float* point_means,
+                     const float* point_colors, const float* inverse_covariance_2d, const float* min_x,
+                     const float* max_x, const float* min_y, const float* max_y, const float* opacity,
+                     const GsbParams* prm_in, float* out_image, void* stream) {
+  if (!c || !prm_in || !out_image || m < 0) return GSB_E_INVALID_ARG;
+  if (m > 0 && (!point_means || !point_colors || !inverse_covariance_2d || !min_x || !max_x || !min_y || !max_y || !opacity))
+    return GSB_E_INVALID_ARG;
+  GsbParams prm = *prm_in;
+  prm.tile_size = tile_size;
+  GsbCamera cam{};
+  cam.width = W; cam.height = H;
+  GSB_TRY(check_params(&cam, &prm));
+  if (m >= ((int64_t)1 << 31)) return GSB_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const bool cu = prm.semantics == GSB_SEM_REF_CU;
+  const int cover = cu ? 1 : prm.full_cover;  // render.cu covers every pixel (:119-124)
+  FrameGeom geom{W, H, tile_grid_dim(W, kTile, cover), tile_grid_dim(H, kTile, cover)};
+  c->have_frame = false;
+  c->have_order = false;
+  std::memset(&c->info, 0, sizeof(c->info));
+  c->info.n = m; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
+  for (bool& v : c->ev_valid) v = false;
+  StageTimer tm{c, st, prm.collect_stage_times != 0};
+  int launches = 0;
+
+  // stage host inputs
+  const float* src[8] = {point_means, point_colors, inverse_covariance_2d, min_x, max_x, min_y, max_y, opacity};
+  const int width[8] = {2, 3, 4, 1, 1, 1, 1, 1};
+  const float* dev[8];
+  size_t need = 0;
+  for (int i = 0; i < 8; ++i)
+    if (m > 0 && !is_device_pointer(src[i])) need += (size_t)m * width[i] * 4;
+  if (need) GSB_TRY(c->staging.ensure(need));
+  size_t off = 0;
+  for (int i = 0; i < 8; ++i) {
+    if (m == 0 || is_device_pointer(src[i])) { dev[i] = src[i]; continue; }
+    float* d = reinterpret_cast<float*>(c->staging.as<char>() + off);
+    GSB_CUDA_TRY(cudaMemcpyAsync(d, src[i], (size_t)m * width[i] * 4, cudaMemcpyHostToDevice, st));
+    dev[i] = d;
+    off += (size_t)m * width[i] * 4;
+  }
+  const size_t rows = (size_t)(m > 0 ? m : 1);
+  GSB_TRY(c->depth_key.ensure(rows * 4));
+  GSB_TRY(c->rec.ensure(rows * 48));
+  GSB_TRY(c->rect.ensure(rows * 8));
+  GSB_TRY(c->count.ensure(rows * 4));
+  GSB_TRY(c->bbox.ensure(rows * 16));
+  const size_t scan_words = scan_status_words(m);
+  const size_t ctl_words = kCtlHeaderWords + scan_words;
+  GSB_TRY(c->control.ensure(ctl_words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, ctl_words * 4, st));
+  uint32_t* hdr = c->control.as<uint32_t>();
+  tm.mark(0);
+  GSB_CUDA_TRY((cudaError_t)launch_ingest_preprocessed(m, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], geom,
+                                                       prm, c->depth_key.as<uint32_t>(), c->rec.as<float4>(),
+                                                       c->bbox.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), st));
+  if (m > 0) ++launches;
+  tm.mark(GSB_STAGE_PROJECT + 1);
+  GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, geom, hdr, hdr + kCtlHeaderWords, st, tm, &launches));
+  c->info.m_in_view = m;
+
+  float* dev_image = out_image;
+  const size_t bytes = (size_t)W * H * 3 * sizeof(float);
+  const bool host_out = !is_device_pointer(out_image);
+  if (host_out) { GSB_TRY(c->image.ensure(bytes)); dev_image = c->image.as<float>(); }
+  if (!cover) GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, bytes, st));
+  const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
+  if (cu)
+    GSB_CUDA_TRY((cudaError_t)launch_composite_cu(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), c->bbox.as<float4>(),
+                                                  dev_image, geom, prm, st));
+  else
+    GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, prm, st));
+  if (geom.tiles_x * geom.tiles_y > 0) ++launches;
+  tm.mark(GSB_STAGE_COMPOSITE + 1);
+  if (host_out) GSB_CUDA_TRY(cudaMemcpyAsync(out_image, dev_image, bytes, cudaMemcpyDeviceToHost, st));
+  c->info.kernel_launches = launches;
+  c->frame_rows = m;
+  c->have_frame = true;
+  finish_times(c, st, tm.on);
+  return GSB_OK;
+}
+
+int gsb_frame_info(GsbContext* c, GsbFrameInfo* info) {
+  if (!c || !info) return GSB_E_INVALID_ARG;
+  if (!c->have_frame) return GSB_E_NO_FRAME;
+  *info = c->info;
+  return GSB_OK;
+}
+
+}  // extern "C"
+
+// ---- debug getters ---------------------------------------------------------------------------------
+namespace {
+__global__ void unpack_projection_kernel(int64_t n, const uint32_t* __restrict__ depth_key, const float4* __restrict__ rec,
+                                         const ushort4* __restrict__ rect, const uint32_t* __restrict__ count,
+                                         uint8_t* in_view, float* depth, float* pxy, float* radius, int32_t* trect) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool keep = depth_key[i] != 0xFFFFFFFFu;
+  in_view[i] = keep ? 1 : 0;
+  float4 r0 = make_float4(0, 0, 0, 0), r2 = r0;
+  if (keep) { r0 = rec[3 * i]; r2 = rec[3 * i + 2]; }
+  depth[i] = keep ? __uint_as_float(depth_key[i]) : 0.f;
+  pxy[2 * i] = r0.x; pxy[2 * i + 1] = r0.y;
+  radius[i] = r2.y;
+  const ushort4 r = rect[i];
+  const bool any = keep && count[i] > 0;
+  trect[4 * i + 0] = any ? r.x : 0; trect[4 * i + 1] = any ? r.y : -1;
+  trect[4 * i + 2] = any ? r.z : 0; trect[4 * i + 3] = any ? r.w : -1;
+}
+}  // namespace
+
+extern "C" {
+
+int gsb_debug_projection(GsbContext* c, uint8_t* in_view, float* depth, float* points_xy, float* radius,
+                         int32_t* tile_rect, uint32_t* tile_count) {
+  if (!c) return GSB_E_INVALID_ARG;
+  if (!c->have_frame) return GSB_E_NO_FRAME;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t n = c->frame_rows;
+  if (n == 0) return GSB_OK;
+  // staging: u8[n] (padded to 4) | depth | pxy | radius | rect
+  const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
+  GSB_TRY(c->scratch.ensure(n4 + (size_t)n * 4 * (1 + 2 + 1 + 4)));
+  uint8_t* s_v = c->scratch.as<uint8_t>();
+  float* s_d = reinterpret_cast<float*>(s_v + n4);
+  float* s_xy = s_d + n; float* s_r = s_xy + 2 * n; int32_t* s_t = reinterpret_cast<int32_t*>(s_r + n);
+  unpack_projection_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, c->depth_key.as<uint32_t>(), c->rec.as<float4>(),
+                                                                c->rect.as<ushort4>(), c->count.as<uint32_t>(), s_v, s_d,
+                                                                s_xy, s_r, s_t);
+  GSB_CUDA_TRY(cudaGetLastError());
+  if (in_view) GSB_CUDA_TRY(cudaMemcpy(in_view, s_v, (size_t)n, cudaMemcpyDefault));
+  if (depth) GSB_CUDA_TRY(cudaMemcpy(depth, s_d, (size_t)n * 4, cudaMemcpyDefault));
+  if (points_xy) GSB_CUDA_TRY(cudaMemcpy(points_xy, s_xy, (size_t)n * 8, cudaMemcpyDefault));
+  if (radius) GSB_CUDA_TRY(cudaMemcpy(radius, s_r, (size_t)n * 4, cudaMemcpyDefault));
+  if (tile_rect) GSB_CUDA_TRY(cudaMemcpy(tile_rect, s_t, (size_t)n * 16, cudaMemcpyDefault));
+  if (tile_count) GSB_CUDA_TRY(cudaMemcpy(tile_count, c->count.p, (size_t)n * 4, cudaMemcpyDefault));
+  return GSB_OK;
+}
+
+int gsb_debug_sorted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
+  if (!c) return GSB_E_INVALID_ARG;
+  if (!c->have_frame) return GSB_E_NO_FRAME;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const size_t k = (size_t)c->info.k_instances;
+  if (k == 0) return GSB_OK;
+  if (keys) GSB_CUDA_TRY(cudaMemcpy(keys, c->sorted_in_a ? c->keys_a.p : c->keys_b.p, k * 8, cudaMemcpyDefault));
+  if (payload) GSB_CUDA_TRY(cudaMemcpy(payload, c->sorted_in_a ? c->vals_a.p : c->vals_b.p, k * 4, cudaMemcpyDefault));
+  return GSB_OK;
+}
+
+int gsb_debug_emitted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
+  if (!c) return GSB_E_INVALID_ARG;
+  if (!c->have_frame || !c->emitted_valid) return GSB_E_NO_FRAME;  // multi-pass sorts recycle the emit buffer
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const size_t k = (size_t)c->info.k_instances;
+  if (k == 0) return GSB_OK;
+  if (keys) GSB_CUDA_TRY(cudaMemcpy(keys, c->keys_a.p, k * 8, cudaMemcpyDefault));
+  if (payload) GSB_CUDA_TRY(cudaMemcpy(payload, c->vals_a.p, k * 4, cudaMemcpyDefault));
+  return GSB_OK;
+}
+
+int gsb_debug_tile_ranges(GsbContext* c, uint32_t* ranges) {
+  if (!c || !ranges) return GSB_E_INVALID_ARG;
+  if (!c->have_frame) return GSB_E_NO_FRAME;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const size_t tiles = (size_t)c->info.tiles_x * c->info.tiles_y;
+  if (tiles == 0) return GSB_OK;
+  GSB_CUDA_TRY(cudaMemcpy(ranges, c->ranges.p, tiles * 8, cudaMemcpyDefault));
+  return GSB_OK;
+}
+
+int gsb_stage_times(GsbContext* c, float ms[GSB_NUM_STAGES]) {
+  if (!c || !ms) return GSB_E_INVALID_ARG;
+  if (!c->have_frame || !c->have_times) return GSB_E_NO_FRAME;
+  for (int i = 0; i < GSB_NUM_STAGES; ++i) ms[i] = c->stage_ms[i];
+  return GSB_OK;
+}
+
+int gsb_sort_pairs_u64(GsbContext* c, int64_t n, uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out,
+                       uint32_t* vals_out, int32_t begin_bit, int32_t end_bit, void* stream) {
+  if (!c || n < 0 || begin_bit < 0 || end_bit > 64 || end_bit < begin_bit) return GSB_E_INVALID_ARG;
+  if (n >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;
+  if (n > 0 && (!keys_in || !vals_in || !keys_out || !vals_out)) return GSB_E_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  if (n == 0) return GSB_OK;
+  SortPlan plan = make_sort_plan<uint64_t>(n, begin_bit, end_bit);
+  GSB_TRY(c->control2.ensure(plan.control_words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+  bool in_a = true;
+  int launches = 0;
+  GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, keys_in, vals_in, keys_out, vals_out, c->control2.as<uint32_t>(),
+                                                  &in_a, &launches, st));
+  if (in_a) {  // even number of passes (or none): result sits in the input buffers
+    GSB_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return GSB_OK;
+}
+
+}  // extern "C"

@@ -254,7 +254,7 @@ int launch_sort(const SortPlan& plan, KeyT* keys_a, uint32_t* vals_a, KeyT* keys
   uint32_t* hist = control;
   uint32_t* tickets = control + (size_t)kMaxPasses * kRadix;
   uint32_t* status = tickets + 8;
-  int hist_blocks = (int)min<int64_t>(plan.tiles, 148 * 4);
+  int hist_blocks = plan.tiles < 148 * 4 ? (int)plan.tiles : 148 * 4;
   histogram_kernel<KeyT><<<hist_blocks, kThreads, 0, st>>>(keys_a, plan.n, plan.begin_bit, plan.end_bit, plan.passes, hist);
   if (launches) ++*launches;
   KeyT* kin = keys_a; KeyT* kout = keys_b;

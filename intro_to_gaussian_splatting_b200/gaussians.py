@@ -1,0 +1,43 @@
+"""Gaussian parameter container (splat/gaussians.py:9-69): same constructor, same attributes."""
+
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from .utils import build_rotation, inverse_sigmoid
+
+
+class Gaussians(nn.Module):
+    """points (N,3); colors (N,3) stored as rgb/256; scales (N,3) LINEAR, default 0.001;
+    quaternions (N,4) wxyz, default identity; opacity (N,1) logit, default logit(0.9999)
+    (splat/gaussians.py:19-33).  Overwrite the attributes to load a trained / synthetic set.
+
+    The reference ctor also writes `<model_path>/point_cloud.ply` through a Python tuple loop
+    (splat/gaussians.py:17-18, splat/utils.py:102-125); nothing reads it back, it needs `plyfile`,
+    and it is outside the render path, so it is not reproduced (out of scope)."""
+
+    def __init__(self, points: torch.Tensor, colors: torch.Tensor, model_path: str = ".") -> None:
+        super().__init__()
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.point_cloud_path = os.path.join(model_path, "point_cloud.ply")
+        self.points = points.clone().requires_grad_(True).to(self.device).float()
+        self.colors = (colors / 256).clone().requires_grad_(True).to(self.device).float()
+        self.scales = torch.ones((len(self.points), 3)).to(self.device).float() * 0.001
+        self.quaternions = torch.zeros((len(self.points), 4)).to(self.device)
+        self.quaternions[:, 0] = 1.0
+        self.opacity = inverse_sigmoid(0.9999 * torch.ones((self.points.shape[0], 1), dtype=torch.float)).to(self.device)
+
+    def get_3d_covariance_matrix(self) -> torch.Tensor:
+        """R S S^T R^T per Gaussian (splat/gaussians.py:54-69).  Kept for API parity; the render
+        path computes this inside csrc/project.cu and never calls it."""
+        q = nn.functional.normalize(self.quaternions, p=2, dim=1)
+        rot = build_rotation(q)
+        s = torch.zeros((len(self.points), 3, 3)).to(self.device)
+        s[:, 0, 0] = self.scales[:, 0]
+        s[:, 1, 1] = self.scales[:, 1]
+        s[:, 2, 2] = self.scales[:, 2]
+        m = rot @ s
+        return m @ m.transpose(1, 2)

@@ -1,0 +1,185 @@
+"""`Rasterizer`: one GsbContext (one CUDA device) behind a small torch-facing class.
+
+PyTorch is plumbing here: it owns device memory and streams; every computation on the render path
+happens inside libgsb_b200.so (csrc/).  All methods raise RuntimeError on failure; there is no
+fallback path of any kind.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import GsbCamera, GsbFrameInfo, GsbParams, check
+from .schema import PreprocessedScene
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class Rasterizer:
+    def __init__(self, device: Optional[int] = None) -> None:
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("intro_to_gaussian_splatting_b200: no CUDA device; this renderer has no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        check(self._lib.gsb_create(C.byref(h), self.device_index), "gsb_create")
+        self._h = h
+        self.n = 0
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.gsb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene -------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload(self, points, scales, quaternions, colors, opacity) -> None:
+        """Gaussian attributes in the reference's layouts (splat/gaussians.py:19-33); CUDA or CPU tensors."""
+        ts = [_f32c(t) for t in (points, scales, quaternions, colors, opacity)]
+        n = ts[0].shape[0]
+        shapes = [(n, 3), (n, 3), (n, 4), (n, 3)]
+        for t, s in zip(ts[:4], shapes):
+            if tuple(t.shape) != s:
+                raise RuntimeError(f"gsb_upload: expected shape {s}, got {tuple(t.shape)}")
+        if ts[4].numel() != n:
+            raise RuntimeError("gsb_upload: opacity must have N elements")
+        for t in ts:
+            if t.is_cuda and t.device != self.device:
+                raise RuntimeError("gsb_upload: tensors live on a different GPU than the rasterizer")
+        with torch.cuda.device(self.device):
+            check(self._lib.gsb_upload(self._h, n, *[_ptr(t) for t in ts], self._stream()), "gsb_upload")
+            torch.cuda.current_stream(self.device).synchronize()  # inputs may be temporaries
+        self.n = n
+
+    # ---- rendering ---------------------------------------------------------------------------
+    def render(self, cam: GsbCamera, params: Optional[GsbParams] = None, out: Optional[torch.Tensor] = None,
+               layout: str = "hwc") -> torch.Tensor:
+        """One frame.  layout 'hwc' -> (H,W,3) like render.cu; 'whc' -> (W,H,3) like the CPU path;
+        'u8' -> (H,W,3) uint8.  `out` may be a CUDA tensor or a (pinned) CPU tensor."""
+        params = params or _lib.default_params()
+        H, W = cam.height, cam.width
+        shape, dtype = {"hwc": ((H, W, 3), torch.float32), "whc": ((W, H, 3), torch.float32),
+                        "u8": ((H, W, 3), torch.uint8)}[layout]
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+            raise RuntimeError(f"render: out must be contiguous {dtype} of shape {shape}")
+        fn = {"hwc": self._lib.gsb_render, "whc": self._lib.gsb_render_wh, "u8": self._lib.gsb_render_u8}[layout]
+        with torch.cuda.device(self.device):
+            check(fn(self._h, C.byref(cam), C.byref(params), _ptr(out), self._stream()), "gsb_render")
+        return out
+
+    def preprocess(self, cam: GsbCamera, params: Optional[GsbParams] = None, with_source_index: bool = False):
+        params = params or _lib.default_params()
+        n = self.n
+        dev = self.device
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        bufs = dict(points_xy=f(n, 2), colors=f(n, 3), covariance_2d=f(n, 2, 2), depths=f(n),
+                    inverse_covariance_2d=f(n, 2, 2), radius=f(n), min_x=f(n), min_y=f(n), max_x=f(n),
+                    max_y=f(n), sigmoid_opacity=f(n, 1))
+        src = torch.empty(n, dtype=torch.int32, device=dev)
+        m = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsb_preprocess(self._h, C.byref(cam), C.byref(params), C.byref(m),
+                                           *[_ptr(bufs[k]) for k in ("points_xy", "colors", "covariance_2d", "depths",
+                                                                     "inverse_covariance_2d", "radius", "min_x", "min_y",
+                                                                     "max_x", "max_y", "sigmoid_opacity")],
+                                           _ptr(src), self._stream()), "gsb_preprocess")
+        m = m.value
+        b = {k: v[:m] for k, v in bufs.items()}
+        pp = PreprocessedScene(points=b["points_xy"], colors=b["colors"], covariance_2d=b["covariance_2d"],
+                               depths=b["depths"], inverse_covariance_2d=b["inverse_covariance_2d"], radius=b["radius"],
+                               points_xy=b["points_xy"].clone(), min_x=b["min_x"], min_y=b["min_y"], max_x=b["max_x"],
+                               max_y=b["max_y"], sigmoid_opacity=b["sigmoid_opacity"])
+        return (pp, src[:m]) if with_source_index else pp
+
+    def render_preprocessed(self, height: int, width: int, tile_size: int, point_means, point_colors,
+                            inverse_covariance_2d, min_x, max_x, min_y, max_y, opacity,
+                            params: Optional[GsbParams] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference op, argument for argument (splat/c/render.cu:90-101)."""
+        if params is None:
+            params = _lib.default_params(semantics=_lib.GSB_SEM_REF_CU, min_weight=1e-3)  # render.cu:73
+        ts = [_f32c(t) for t in (point_means, point_colors, inverse_covariance_2d, min_x, max_x, min_y, max_y, opacity)]
+        devs = {t.device for t in ts}
+        if len(devs) != 1:  # torch::checkAllSameGPU, render.cu:104-112
+            raise RuntimeError("render_image: all tensors must be on the same device")
+        m = ts[0].shape[0]
+        H, W = int(height), int(width)
+        if out is None:
+            out = torch.empty((H, W, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsb_render_image(self._h, H, W, int(tile_size), m, *[_ptr(t) for t in ts],
+                                             C.byref(params), _ptr(out), self._stream()), "gsb_render_image")
+            torch.cuda.current_stream(self.device).synchronize()  # `ts` may be temporaries
+        return out
+
+    # ---- parity / debug surface ----------------------------------------------------------------
+    def frame_info(self) -> GsbFrameInfo:
+        info = GsbFrameInfo()
+        check(self._lib.gsb_frame_info(self._h, C.byref(info)), "gsb_frame_info")
+        return info
+
+    def debug_projection(self) -> Dict[str, torch.Tensor]:
+        n = int(self.frame_info().n)
+        dev = self.device
+        out = dict(in_view=torch.empty(n, dtype=torch.uint8, device=dev),
+                   depth=torch.empty(n, dtype=torch.float32, device=dev),
+                   points_xy=torch.empty((n, 2), dtype=torch.float32, device=dev),
+                   radius=torch.empty(n, dtype=torch.float32, device=dev),
+                   tile_rect=torch.empty((n, 4), dtype=torch.int32, device=dev),
+                   tile_count=torch.empty(n, dtype=torch.int32, device=dev))
+        check(self._lib.gsb_debug_projection(self._h, *[_ptr(out[k]) for k in
+                                                        ("in_view", "depth", "points_xy", "radius", "tile_rect", "tile_count")]),
+              "gsb_debug_projection")
+        return out
+
+    def debug_sorted_keys(self):
+        k = int(self.frame_info().k_instances)
+        keys = torch.empty(k, dtype=torch.int64, device=self.device)  # bit pattern of the u64 keys
+        payload = torch.empty(k, dtype=torch.int32, device=self.device)
+        check(self._lib.gsb_debug_sorted_keys(self._h, _ptr(keys), _ptr(payload)), "gsb_debug_sorted_keys")
+        return keys, payload
+
+    def debug_tile_ranges(self) -> torch.Tensor:
+        info = self.frame_info()
+        r = torch.empty((info.tiles_x * info.tiles_y, 2), dtype=torch.int32, device=self.device)
+        check(self._lib.gsb_debug_tile_ranges(self._h, _ptr(r)), "gsb_debug_tile_ranges")
+        return r
+
+    def stage_times(self) -> Dict[str, float]:
+        arr = (C.c_float * _lib.GSB_NUM_STAGES)()
+        check(self._lib.gsb_stage_times(self._h, C.byref(arr)), "gsb_stage_times")
+        return {name: float(arr[i]) for i, name in enumerate(_lib.STAGE_NAMES)}
+
+    def sort_pairs(self, keys: torch.Tensor, values: torch.Tensor, begin_bit: int = 0, end_bit: int = 64):
+        """Stable LSD onesweep sort of (int64-bit-pattern keys, int32 payload) on bits [begin,end)."""
+        assert keys.dtype == torch.int64 and values.dtype == torch.int32 and keys.is_cuda and values.is_cuda
+        kin, vin = keys.clone(), values.clone()
+        kout, vout = torch.empty_like(kin), torch.empty_like(vin)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsb_sort_pairs_u64(self._h, kin.numel(), _ptr(kin), _ptr(vin), _ptr(kout), _ptr(vout),
+                                               int(begin_bit), int(end_bit), self._stream()), "gsb_sort_pairs_u64")
+            torch.cuda.current_stream(self.device).synchronize()
+        return kout, vout
