@@ -628,11 +628,12 @@ int gsb_debug_emitted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
 }
 
 int gsb_debug_tile_ranges(GsbContext* c, uint32_t* ranges) {
-  if (!c || !ranges) return GSB_E_INVALID_ARG;
+  if (!c) return GSB_E_INVALID_ARG;
   if (!c->have_frame) return GSB_E_NO_FRAME;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   const size_t tiles = (size_t)c->info.tiles_x * c->info.tiles_y;
   if (tiles == 0) return GSB_OK;
+  if (!ranges) return GSB_E_INVALID_ARG;
   GSB_CUDA_TRY(cudaMemcpy(ranges, c->ranges.p, tiles * 8, cudaMemcpyDefault));
   return GSB_OK;
 }
