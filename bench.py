@@ -60,7 +60,7 @@ def load_peaks():
 
 
 def workload_name(spec):
-    return f"{spec.name}: {spec.n} synthetic Gaussians (synth-v1 seed {spec.seed}), {spec.width}x{spec.height}, {ORBIT}-view orbit"
+    return f"{spec.name}: {spec.n} synthetic Gaussians (synth-v2 seed {spec.seed}), {spec.width}x{spec.height}, {ORBIT}-view orbit"
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -293,11 +293,18 @@ __global__ void gather_preprocess_kernel(const uint32_t* __restrict__ order, int
     colors[3 * j + 2] = planes[PB * n_pad + g];
   }
   if (depths) depths[j] = __uint_as_float(depth_key[g]);
-  if (radius) radius[j] = r2.y;
-  if (sig_op) sig_op[j] = r2.z;
+  if (radius) radius[j] = r2.z;
+  if (sig_op) sig_op[j] = r2.w;
   if (src_index) src_index[j] = (int32_t)g;
-  if (cov2d) reinterpret_cast<float4*>(cov2d)[j] = reinterpret_cast<const float4*>(dbg.cov2d)[g];
-  if (conic) reinterpret_cast<float4*>(conic)[j] = reinterpret_cast<const float4*>(dbg.conic)[g];
+  // destinations are packed back to back in one staging block: only 4-byte alignment is guaranteed
+  if (cov2d) {
+    const float4 v = reinterpret_cast<const float4*>(dbg.cov2d)[g];
+    cov2d[4 * j] = v.x; cov2d[4 * j + 1] = v.y; cov2d[4 * j + 2] = v.z; cov2d[4 * j + 3] = v.w;
+  }
+  if (conic) {
+    const float4 v = reinterpret_cast<const float4*>(dbg.conic)[g];
+    conic[4 * j] = v.x; conic[4 * j + 1] = v.y; conic[4 * j + 2] = v.z; conic[4 * j + 3] = v.w;
+  }
   const float4 bb = reinterpret_cast<const float4*>(dbg.bbox)[g];
   if (min_x) min_x[j] = bb.x;
   if (min_y) min_y[j] = bb.y;

@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(256)
 composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
                  const float4* __restrict__ rec, const float4* __restrict__ bbox, float* __restrict__ image,
                  const __grid_constant__ CompositeArgs a) {
-  __shared__ float4 s0[kBatch];  // mx, my, qa, qb
-  __shared__ float4 s1[kBatch];  // qc, op, r, g
-  __shared__ float s2[kBatch];   // b
+  __shared__ float4 s0[kBatch];  // mx, my, a, b      (a b; c d) = -0.5 * inverse covariance
+  __shared__ float4 s1[kBatch];  // c, d, op, r
+  __shared__ float2 s2[kBatch];  // g, b
   __shared__ float4 s3[kSem == GSB_SEM_REF_CU ? kBatch : 1];  // bbox (REF_CU only)
 
   const int tile = blockIdx.x;
@@ -70,7 +70,7 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     if (kSem == GSB_SEM_REF_CU) r3 = bbox[g];
   }
   for (uint32_t b0 = 0; b0 < len; b0 += kBatch) {
-    s0[tid] = r0; s1[tid] = r1; s2[tid] = r2.x;
+    s0[tid] = r0; s1[tid] = r1; s2[tid] = make_float2(r2.x, r2.y);
     if (kSem == GSB_SEM_REF_CU) s3[tid] = r3;
     __syncthreads();
     const uint32_t nxt = b0 + kBatch + tid;
@@ -90,15 +90,22 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
           if (fx < bb.x || fx > bb.z || fy < bb.y || fy > bb.w) continue;
         }
         const float dx = g0.x - fx, dy = g0.y - fy;
-        const float p = dx * (g0.z * dx + g0.w * dy) + (g1.x * dy) * dy;
-        float alpha = ex2_approx(p) * g1.y;
+        // The reference's own rounding sequence (compute_gaussian_weight, splat/utils.py:363-364), probed
+        // bit-exact against torch on ill-conditioned conics: ((-0.5 d) @ inv) is an FMA chain in k order,
+        // (.) @ d^T is two rounded products and a rounded sum.  Long thin Gaussians make this sum cancel
+        // catastrophically, so any other order drifts from the reference by far more than 1e-4.
+        const float u0 = __fmaf_rn(dy, g1.x, __fmul_rn(dx, g0.z));
+        const float u1 = __fmaf_rn(dy, g1.y, __fmul_rn(dx, g0.w));
+        const float power = __fadd_rn(__fmul_rn(u0, dx), __fmul_rn(u1, dy));
+        float alpha = ex2_approx(power * 1.4426950408889634f) * g1.z;
         if (kSem == GSB_SEM_REF_CU) alpha = fminf(a.alpha_max, alpha);
         const float ta = T * alpha;
         const float test = T - ta;
         if (test < a.min_weight) { done = true; break; }
-        cr = fmaf(ta, g1.z, cr);
-        cg = fmaf(ta, g1.w, cg);
-        cb = fmaf(ta, s2[i], cb);
+        const float2 gb = s2[i];
+        cr = fmaf(ta, g1.w, cr);
+        cg = fmaf(ta, gb.x, cg);
+        cb = fmaf(ta, gb.y, cb);
         T = test;
       }
     }
@@ -147,7 +154,6 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
               float4* __restrict__ bbox, ushort4* __restrict__ rect, uint32_t* __restrict__ count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const float kq = -0.72134752044448170368f;
   const float mx = means[2 * i], my = means[2 * i + 1];
   const float i00 = conic[4 * i], i01 = conic[4 * i + 1], i10 = conic[4 * i + 2], i11 = conic[4 * i + 3];
   const float mnx = min_x[i], mxx = max_x[i], mny = min_y[i], mxy = max_y[i];
@@ -155,10 +161,13 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
   int tx0, tx1, ty0, ty1;
   bool nan = !(mnx == mnx) || !(mxx == mxx) || !(mny == mny) || !(mxy == mxy);
   const float big = 1073741824.0f;
+  float op_used;
   if (sem == GSB_SEM_REF_CU) {
-    // render.cu:55-60: pixel p is a candidate iff min <= p <= max (inclusive, per pixel); mean -> int (:8-9)
-    rec[3 * i + 0] = make_float4(truncf(mx), truncf(my), kq * i00, kq * (2.0f * i01));
-    rec[3 * i + 1] = make_float4(kq * i11, op, colors[3 * i], colors[3 * i + 1]);
+    // render.cu:55-60: pixel p is a candidate iff min <= p <= max (inclusive, per pixel); mean -> int (:8-9);
+    // power = dx*a*dx + 2*dx*dy*b + dy*dy*c with inv[0], inv[1], inv[3] (:17,:66-68)  ==  d^T [[a,b],[b,c]] d
+    rec[3 * i + 0] = make_float4(truncf(mx), truncf(my), -0.5f * i00, -0.5f * i01);
+    rec[3 * i + 1] = make_float4(-0.5f * i01, -0.5f * i11, op, colors[3 * i]);
+    op_used = op;
     int x0 = (int)ceilf(fminf(fmaxf(mnx, -big), big)), x1 = (int)floorf(fminf(fmaxf(mxx, -big), big));
     int y0 = (int)ceilf(fminf(fmaxf(mny, -big), big)), y1 = (int)floorf(fminf(fmaxf(mxy, -big), big));
     x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, geom.width - 1); y1 = min(y1, geom.height - 1);
@@ -167,14 +176,15 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
     if (y1 < y0) { ty0 = 0; ty1 = -1; }
   } else {
     const float op2 = 1.0f / (1.0f + expf(-op));  // the CPU path applies a second sigmoid (:164)
-    rec[3 * i + 0] = make_float4(mx, my, kq * i00, kq * (i01 + i10));
-    rec[3 * i + 1] = make_float4(kq * i11, op2, colors[3 * i], colors[3 * i + 1]);
+    rec[3 * i + 0] = make_float4(mx, my, -0.5f * i00, -0.5f * i01);
+    rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, op2, colors[3 * i]);
+    op_used = op2;
     int imn = (int)fminf(fmaxf(mnx, -big), big), imx = (int)fminf(fmaxf(mxx, -big), big);
     tx0 = max(floor_div_i(imn - 1, T), 0); tx1 = min(floor_div_i(imx, T), geom.tiles_x - 1);
     imn = (int)fminf(fmaxf(mny, -big), big); imx = (int)fminf(fmaxf(mxy, -big), big);
     ty0 = max(floor_div_i(imn - 1, T), 0); ty1 = min(floor_div_i(imx, T), geom.tiles_y - 1);
   }
-  rec[3 * i + 2] = make_float4(colors[3 * i + 2], 0.f, op, 0.f);
+  rec[3 * i + 2] = make_float4(colors[3 * i + 1], colors[3 * i + 2], 0.f, op_used);
   bbox[i] = make_float4(mnx, mny, mxx, mxy);
   uint32_t cnt = 0;
   if (!nan && tx1 >= tx0 && ty1 >= ty0) cnt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);

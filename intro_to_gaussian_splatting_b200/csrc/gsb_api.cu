@@ -569,7 +569,7 @@ __global__ void unpack_projection_kernel(int64_t n, const uint32_t* __restrict__
   if (keep) { r0 = rec[3 * i]; r2 = rec[3 * i + 2]; }
   depth[i] = keep ? __uint_as_float(depth_key[i]) : 0.f;
   pxy[2 * i] = r0.x; pxy[2 * i + 1] = r0.y;
-  radius[i] = r2.y;
+  radius[i] = r2.z;
   const ushort4 r = rect[i];
   const bool any = keep && count[i] > 0;
   trect[4 * i + 0] = any ? r.x : 0; trect[4 * i + 1] = any ? r.y : -1;

@@ -233,10 +233,10 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       // opacity as the CPU path uses it: sigmoid(sigmoid(logit)) (splat/gaussian_scene.py:143 then :164)
       const float sig1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
       const float op2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sig1)));
-      const float kq = -0.72134752044448170368f;  // -0.5 * log2(e): exp(-q/2) = exp2(kq*q)
-      rec[3 * i + 0] = make_float4(px, py, __fmul_rn(kq, i00), __fmul_rn(kq, __fadd_rn(i01, i10)));
-      rec[3 * i + 1] = make_float4(__fmul_rn(kq, i11), op2, cr, cg);
-      rec[3 * i + 2] = make_float4(cb, rad, sig1, 0.f);
+      // conic pre-scaled by -0.5: exact (power of two), so (-0.5*d) @ inv rounds identically (composite.cu)
+      rec[3 * i + 0] = make_float4(px, py, -0.5f * i00, -0.5f * i01);
+      rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, op2, cr);
+      rec[3 * i + 2] = make_float4(cg, cb, rad, sig1);
       rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
       depth_key[i] = __float_as_uint(vz);
       if (kDebug) {

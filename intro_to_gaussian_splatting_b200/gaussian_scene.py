@@ -65,14 +65,22 @@ class GaussianScene(nn.Module):
             self._rast = Rasterizer()
         return self._rast
 
+    def invalidate(self) -> None:
+        """Force a re-upload of the Gaussian set on the next call (needed only after in-place edits made
+        through `.data`, which do not bump the tensors' version counters)."""
+        self._uploaded_sig = None
+
     def _sync_gaussians(self) -> Rasterizer:
         g = self.gaussians
         ts = (g.points, g.scales, g.quaternions, g.colors, g.opacity)
-        sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+        # identity + version counter of the five tensors; the tensors themselves are kept referenced so
+        # that neither their id() nor their storage address can be recycled by a replacement
         rast = self.rasterizer
-        if sig != self._uploaded_sig:
+        prev = self._uploaded_sig
+        same = prev is not None and all(a is b and a._version == v for a, (b, v) in zip(ts, prev))
+        if not same:
             rast.upload(*ts)
-            self._uploaded_sig = sig
+            self._uploaded_sig = tuple((t, t._version) for t in ts)
         return rast
 
     def _params(self, tile_size: int, semantics: str = "ref_cpu", **over):

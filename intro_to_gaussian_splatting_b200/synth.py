@@ -1,11 +1,13 @@
-"""Synthetic scenes (`synth-v1`) and COLMAP text-model writer.
+"""Synthetic scenes (`synth-v2`) and COLMAP text-model writer.
 
 The reference ships no data (its notebooks fetch the treehill COLMAP scene over
 the network, /root/reference/get_data.sh:1), so every workload here is a seeded
 synthetic Gaussian cloud.  The generator follows SURVEY.md Appendix E exactly:
 all draws come from ONE `torch.Generator().manual_seed(seed)` in the order
-xyz, rgb, scales, quat, opacity, so a (name, seed) pair is reproducible on any
-box with the same torch version.
+xyz, rgb, scales, quat, opacity.  v2 differs from the survey's v1 probe generator in one respect: exp
+and the normal draws are evaluated in float64 (see _exp_portable) so that a (name, seed) pair is
+bit-reproducible on ANY machine -- v1's torch.exp/torch.randn differ in the last bit between CPU ISAs,
+which was caught when the GPU box disagreed with hashes made in the build container.
 
 The scene is handed to the scene API the same way a reference user would do it:
 a COLMAP *text* model directory (`cameras.txt`, `images.txt`; the formats parsed
@@ -21,6 +23,7 @@ import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 
 # The only camera pose published in the reference (treehill image 100,
@@ -102,6 +105,22 @@ def orbit_views(spec: SceneSpec, n_views: Optional[int] = None, period: int = 25
     return out
 
 
+# torch's vectorised fp32 exp / randn kernels pick an ISA-specific code path (AVX2 vs AVX-512) and differ
+# in the last bit between machines, which would make the "same" scene differ between the build container
+# and the GPU box.  Only torch.rand (Mersenne twister + a fixed int->float conversion) and IEEE add/mul are
+# used in fp32; every transcendental is evaluated in float64 by numpy and rounded once to fp32.
+def _exp_portable(x32: torch.Tensor) -> torch.Tensor:
+    return torch.from_numpy(np.exp(x32.numpy().astype(np.float64)).astype(np.float32))
+
+
+def _randn_portable(n: int, c: int, g: torch.Generator) -> torch.Tensor:
+    """Box-Muller on two torch.rand draws, evaluated in float64."""
+    u1 = torch.rand(n, c, generator=g).numpy().astype(np.float64)
+    u2 = torch.rand(n, c, generator=g).numpy().astype(np.float64)
+    z = np.sqrt(-2.0 * np.log1p(-u1)) * np.cos(2.0 * np.pi * u2)
+    return torch.from_numpy(z.astype(np.float32))
+
+
 def make_scene(spec_or_name, n_views: Optional[int] = None, n_override: Optional[int] = None) -> SynthScene:
     spec = CONFIGS[spec_or_name] if isinstance(spec_or_name, str) else spec_or_name
     n = spec.n if n_override is None else n_override
@@ -110,16 +129,16 @@ def make_scene(spec_or_name, n_views: Optional[int] = None, n_override: Optional
     rgb = torch.rand(n, 3, generator=g) * 255
     if spec.log_scale_range is not None:
         lo, hi = spec.log_scale_range
-        scales = torch.exp(torch.rand(n, 3, generator=g) * (hi - lo) + lo)
+        scales = _exp_portable(torch.rand(n, 3, generator=g) * (hi - lo) + lo)
     else:
         scales = torch.ones(n, 3) * (spec.const_scale if spec.const_scale is not None else 0.001)
     if spec.random_quat:
-        quats = torch.randn(n, 4, generator=g)
+        quats = _randn_portable(n, 4, g)
     else:
         quats = torch.zeros(n, 4)
         quats[:, 0] = 1.0
     if spec.random_opacity:
-        opacity = torch.randn(n, 1, generator=g) * 2 + 1
+        opacity = _randn_portable(n, 1, g) * 2 + 1
     else:
         x = 0.9999 * torch.ones((n, 1), dtype=torch.float)
         opacity = torch.log(x / (1 - x))  # inverse_sigmoid, splat/utils.py:128-129

@@ -195,14 +195,14 @@ def tile_ranges(sorted_keys: np.ndarray, ntiles: int) -> np.ndarray:
     return r[:ntiles]
 
 
-def composite(cam: Camera, prm: Params, ranges, payload, pr: Projection):
+def composite(cam: Camera, prm: Params, ranges, payload, pr: Projection, steps_per_pixel=None):
     """REF_CPU compositing -> ((H,W,3) image, executed steps)."""
     img = np.zeros((cam.height, cam.width, 3), np.float32)
     steps = C.c_int64(0)
     ranges = np.ascontiguousarray(ranges, np.uint32)
     payload = np.ascontiguousarray(payload, np.uint32)
     lib().orc_composite(C.byref(cam), C.byref(prm), _p(ranges), _p(payload), _p(pr.pxy), _p(pr.conic),
-                        _p(pr.colors), _p(pr.sig_op), _p(img), C.byref(steps))
+                        _p(pr.colors), _p(pr.sig_op), _p(img), C.byref(steps), _p(steps_per_pixel))
     return img, steps.value
 
 

@@ -44,9 +44,14 @@ def test_reupload_when_attributes_change():
     scene.gaussians.opacity = scene.gaussians.opacity - 3.0
     b = scene.render_image_cuda(1)
     assert not torch.equal(a, b)
-    scene.gaussians.colors.data.mul_(0.5)  # in-place edit bumps the version counter
+    with torch.no_grad():
+        scene.gaussians.colors.mul_(0.5)  # in-place edit bumps the version counter
     c = scene.render_image_cuda(1)
     assert torch.allclose(c, b * 0.5, atol=1e-6)
+    scene.gaussians.colors.data.mul_(2.0)  # edits through .data are invisible to autograd's counter ...
+    scene.invalidate()                      # ... so the scene has to be told
+    d = scene.render_image_cuda(1)
+    assert torch.allclose(d, b, atol=1e-6)
 
 
 def test_reference_op_signature_ref_cu():

@@ -178,7 +178,7 @@ def test_sort_standalone(rast):
         for (b, e) in [(0, 64), (0, 45), (32, 45), (3, 20)]:
             keys = torch.randint(-(2 ** 62), 2 ** 62, (n,), generator=g, dtype=torch.int64)
             if n > 10:
-                keys[n // 2:] = keys[: n - n // 2]  # plenty of duplicates: stability matters
+                keys[n // 2:] = keys[: n - n // 2].clone()  # plenty of duplicates: stability matters
             vals = torch.arange(n, dtype=torch.int32)
             ko, vo = rast.sort_pairs(keys.cuda(), vals.cuda(), b, e)
             ku = keys.numpy().view(np.uint64)
