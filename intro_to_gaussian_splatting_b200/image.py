@@ -18,31 +18,42 @@ class GaussianImage(torch.nn.Module):
     def __init__(self, camera: Camera, image: Image) -> None:
         super().__init__()
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        dev = self.device
-        self.f_x = torch.Tensor([camera.params[0]]).to(dev)
-        self.f_y = torch.Tensor([camera.params[1]]).to(dev)
-        self.c_x = torch.Tensor([camera.params[2]]).to(dev)
-        self.c_y = torch.Tensor([camera.params[3]]).to(dev)
-        self.R = build_rotation(torch.Tensor(image.qvec).unsqueeze(0)).to(dev)
-        self.T = torch.Tensor(image.tvec).to(dev)
-        self.height = torch.Tensor([camera.height]).to(dev)
-        self.width = torch.Tensor([camera.width]).to(dev)
-        self.fovX = focal2fov(self.f_x, self.width).to(dev)
-        self.fovY = focal2fov(self.f_y, self.height).to(dev)
-        self.tan_fovX = torch.tan(self.fovX / 2).to(dev)
-        self.tan_fovY = torch.tan(self.fovY / 2).to(dev)
-        self.zfar = torch.Tensor([100.0]).to(dev)   # splat/image.py:46-47
-        self.znear = torch.Tensor([0.001]).to(dev)
-        self.name = image.name
+        # Every constant is computed ON THE CPU with the reference's op sequence and only then moved to
+        # `self.device`.  The reference evaluates tan / bmm on whatever device it runs on, and CUDA's tan and
+        # cuBLAS' 4x4 product differ from the CPU's in the last bit; the parity target is the CPU path, so the
+        # CPU values are the contract (a 1-ulp tan_fovX moves the fov clamp of compute_2d_covariance).
+        f_x = torch.Tensor([camera.params[0]])
+        f_y = torch.Tensor([camera.params[1]])
+        c_x = torch.Tensor([camera.params[2]])
+        c_y = torch.Tensor([camera.params[3]])
+        R = build_rotation(torch.Tensor(image.qvec).unsqueeze(0))
+        T = torch.Tensor(image.tvec)
+        height = torch.Tensor([camera.height])
+        width = torch.Tensor([camera.width])
+        fovX = focal2fov(f_x, width)
+        fovY = focal2fov(f_y, height)
+        tan_fovX = torch.tan(fovX / 2)
+        tan_fovY = torch.tan(fovY / 2)
+        zfar = torch.Tensor([100.0])   # splat/image.py:46-47
+        znear = torch.Tensor([0.001])
         # row-vector convention: row = [x y z 1] @ M   (splat/image.py:51-65)
-        self.world2view = getWorld2View(R=self.R[0], t=self.T).transpose(0, 1).to(dev)
-        self.projection_matrix = (
-            getProjectionMatrix(znear=self.znear, zfar=self.zfar, fovX=self.fovX, fovY=self.fovY).transpose(0, 1).to(dev)
-        )
-        self.full_proj_transform = (
-            self.world2view.unsqueeze(0).bmm(self.projection_matrix.unsqueeze(0)).squeeze(0).to(dev)
-        )
-        self.camera_center = self.world2view.inverse()[3, :3].to(dev)
+        world2view = getWorld2View(R=R[0], t=T).transpose(0, 1)
+        projection_matrix = getProjectionMatrix(znear=znear, zfar=zfar, fovX=fovX, fovY=fovY).transpose(0, 1)
+        full_proj_transform = world2view.unsqueeze(0).bmm(projection_matrix.unsqueeze(0)).squeeze(0)
+        camera_center = world2view.inverse()[3, :3]
+
+        dev = self.device
+        self.f_x, self.f_y, self.c_x, self.c_y = f_x.to(dev), f_y.to(dev), c_x.to(dev), c_y.to(dev)
+        self.R, self.T = R.to(dev), T.to(dev)
+        self.height, self.width = height.to(dev), width.to(dev)
+        self.fovX, self.fovY = fovX.to(dev), fovY.to(dev)
+        self.tan_fovX, self.tan_fovY = tan_fovX.to(dev), tan_fovY.to(dev)
+        self.zfar, self.znear = zfar.to(dev), znear.to(dev)
+        self.name = image.name
+        self.world2view = world2view.contiguous().to(dev)
+        self.projection_matrix = projection_matrix.contiguous().to(dev)
+        self.full_proj_transform = full_proj_transform.contiguous().to(dev)
+        self.camera_center = camera_center.to(dev)
         self._packed = None
 
     def pack(self) -> GsbCamera:

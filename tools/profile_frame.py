@@ -1,0 +1,41 @@
+"""Render a few frames of one config (for ncu / compute-sanitizer runs; not a benchmark)."""
+import argparse
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from intro_to_gaussian_splatting_b200 import Rasterizer, _lib  # noqa: E402
+from intro_to_gaussian_splatting_b200.colmap_io import read_camera_file, read_image_file  # noqa: E402
+from intro_to_gaussian_splatting_b200.image import GaussianImage  # noqa: E402
+from intro_to_gaussian_splatting_b200.synth import CONFIGS, make_scene, write_colmap_text  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="cfg3")
+ap.add_argument("--frames", type=int, default=3)
+ap.add_argument("--sort-mode", default="auto")
+ap.add_argument("--full-cover", type=int, default=1)
+ap.add_argument("--stage-times", type=int, default=0)
+a = ap.parse_args()
+sc = make_scene(CONFIGS[a.config], n_views=max(a.frames, 1))
+d = tempfile.mkdtemp()
+write_colmap_text(sc, d)
+cams, imgs = read_camera_file(d), read_image_file(d)
+packed = [GaussianImage(cams[imgs[i].camera_id], imgs[i]).pack() for i in sorted(imgs)]
+r = Rasterizer(0)
+r.upload(sc.xyz.cuda(), sc.scales.cuda(), sc.quats.cuda(), (sc.rgb255 / 256).float().cuda(), sc.opacity_logit.cuda())
+mode = {"auto": 0, "full": 1, "split": 2}[a.sort_mode]
+prm = _lib.default_params(full_cover=a.full_cover, sort_mode=mode, collect_stage_times=a.stage_times)
+img = torch.empty((sc.spec.height, sc.spec.width, 3), device="cuda")
+for f in range(a.frames):
+    r.render(packed[f], prm, out=img)
+    torch.cuda.synchronize()
+    info = r.frame_info()
+    msg = f"frame {f}: M={info.m_in_view} K={info.k_instances} launches={info.kernel_launches}"
+    if a.stage_times:
+        msg += " " + " ".join(f"{k}={v * 1e3:.1f}us" for k, v in r.stage_times().items())
+    print(msg, flush=True)
