@@ -44,6 +44,7 @@ extern "C" {
 #define GSB_E_UNSUPPORTED (-4)   /* e.g. tile_size != 16, image too large for the key layout */
 #define GSB_E_NO_DEVICE (-5)     /* no usable CUDA device: the library has NO CPU fallback */
 #define GSB_E_ALLOC (-6)
+#define GSB_E_INTERNAL (-7)   /* a device-side consistency check failed */
 
 /* ---- compositing semantics ---- */
 #define GSB_SEM_REF_CPU 0 /* splat/gaussian_scene.py:146-238: the parity target */

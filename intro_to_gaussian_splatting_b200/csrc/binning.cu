@@ -135,65 +135,124 @@ int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t
 
 // ------------------------------------------------------------------------------------------------
 // emit: output-parallel expansion.  A block owns 256 consecutive Gaussians (in emission order) and
-// walks ITS OUTPUT RANGE with coalesced stores; each output slot finds its Gaussian by binary search
-// over the block's 256 offsets in shared memory, so a Gaussian covering 2 000 tiles costs the same
-// per key as one covering 4.
+// walks ITS OUTPUT RANGE in aligned groups of four slots per thread: one binary search over the block's
+// 256 offsets (shared memory) and one division locate the first slot of a group, the other three follow
+// by stepping through the rect (and on to the next Gaussian), and a full group leaves as 16/32-byte
+// vector stores.  A Gaussian covering 2 000 tiles costs the same per key as one covering 4.
+//   kCombined = false (FULL):  keys[o] = tile << 32 | depth bits,  payload[o] = Gaussian index
+//   kCombined = true  (SPLIT): keys[o] = tile << 32 | Gaussian index  (depth order is the emission order;
+//                              the radix passes sort the tile field only and carry the index inside the key)
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
+template <bool kCombined>
 __global__ void __launch_bounds__(kEmitThreads)
 emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
-            int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect,
-            const uint32_t* __restrict__ count, int tiles_x, uint64_t* __restrict__ keys,
-            uint32_t* __restrict__ payload) {
+            int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
+            uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
   __shared__ uint32_t s_off[kEmitThreads + 1];
   __shared__ uint32_t s_gid[kEmitThreads];
-  __shared__ uint32_t s_depth[kEmitThreads];
+  __shared__ uint32_t s_low[kEmitThreads];  // low key word: depth bits (FULL) or Gaussian index (SPLIT)
   __shared__ ushort4 s_rect[kEmitThreads];
   const int64_t base = (int64_t)blockIdx.x * kEmitThreads;
   const int64_t i = base + threadIdx.x;
-  uint32_t off = 0, g = 0;
+  uint32_t off = 0;
   if (i < n) {
-    g = perm ? perm[i] : (uint32_t)i;
+    const uint32_t g = perm ? perm[i] : (uint32_t)i;
     off = offsets[i];
     s_gid[threadIdx.x] = g;
-    s_depth[threadIdx.x] = depth_key[g];
+    s_low[threadIdx.x] = kCombined ? g : depth_key[g];
     s_rect[threadIdx.x] = rect[g];
   }
   const uint32_t k_total = *total;
   s_off[threadIdx.x] = (i < n) ? off : k_total;
   if (threadIdx.x == 0) {
-    int64_t nxt = base + kEmitThreads;
+    const int64_t nxt = base + kEmitThreads;
     s_off[kEmitThreads] = (nxt < n) ? offsets[nxt] : k_total;
   }
   __syncthreads();
   const uint32_t begin = s_off[0], end = s_off[kEmitThreads];
-  for (uint32_t o = begin + threadIdx.x; o < end; o += kEmitThreads) {
-    // largest j with s_off[j] <= o  (entries with count 0 share their successor's offset and lose)
-    int lo = 0, hi = kEmitThreads;  // invariant: s_off[lo] <= o < s_off[hi]
+  for (uint32_t o4 = (begin & ~3u) + 4u * threadIdx.x; o4 < end; o4 += 4u * kEmitThreads) {
+    const uint32_t first = o4 > begin ? o4 : begin;
+    const uint32_t last = (o4 + 4u < end) ? o4 + 4u : end;  // exclusive
+    if (first >= last) continue;
+    // largest j with s_off[j] <= first  (entries with count 0 share their successor's offset and lose)
+    int lo = 0, hi = kEmitThreads;  // invariant: s_off[lo] <= first < s_off[hi]
 #pragma unroll
     for (int step = 0; step < 8; ++step) {
-      int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= o) lo = mid; else hi = mid;
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= first) lo = mid; else hi = mid;
     }
-    const ushort4 r = s_rect[lo];
-    const uint32_t t = o - s_off[lo];
+    ushort4 r = s_rect[lo];
+    uint32_t nxt_off = s_off[lo + 1];
+    const uint32_t t = first - s_off[lo];
     const uint32_t w = (uint32_t)r.y - (uint32_t)r.x + 1u;
-    const uint32_t ty = (uint32_t)r.z + t / w;
-    const uint32_t tx = (uint32_t)r.x + t % w;
-    const uint32_t tile = ty * (uint32_t)tiles_x + tx;
-    keys[o] = ((uint64_t)tile << 32) | (uint64_t)s_depth[lo];
-    payload[o] = s_gid[lo];
+    uint32_t ty = (uint32_t)r.z + t / w;
+    uint32_t tx = (uint32_t)r.x + t % w;
+    uint64_t kv[4];
+    uint32_t pv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t slot = o4 + q;
+      kv[q] = 0; pv[q] = 0;
+      if (slot >= first && slot < last) {
+        while (slot >= nxt_off) {  // move on to the next Gaussian with a non-empty rect
+          ++lo;
+          nxt_off = s_off[lo + 1];
+          r = s_rect[lo];
+          tx = r.x; ty = r.z;
+        }
+        kv[q] = ((uint64_t)(ty * (uint32_t)tiles_x + tx) << 32) | (uint64_t)s_low[lo];
+        pv[q] = s_gid[lo];
+        if (++tx > (uint32_t)r.y) { tx = r.x; ++ty; }
+      }
+    }
+    if (first == o4 && last == o4 + 4u) {
+      ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + o4);  // o4 % 4 == 0: 32-byte aligned
+      kp[0] = make_ulonglong2(kv[0], kv[1]);
+      kp[1] = make_ulonglong2(kv[2], kv[3]);
+      if (!kCombined) *reinterpret_cast<uint4*>(payload + o4) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t slot = o4 + q;
+        if (slot >= first && slot < last) {
+          keys[slot] = kv[q];
+          if (!kCombined) payload[slot] = pv[q];
+        }
+      }
+    }
   }
-  (void)count;
 }
 
 int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
-                const uint32_t* depth_key, const ushort4* rect, const uint32_t* count, int tiles_x,
-                uint64_t* keys, uint32_t* payload, cudaStream_t st) {
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
+                uint32_t* payload, cudaStream_t st) {
   if (n == 0) return 0;
   unsigned blocks = (unsigned)((n + kEmitThreads - 1) / kEmitThreads);
-  emit_kernel<<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, count, tiles_x, keys, payload);
+  if (combined)
+    emit_kernel<true><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
+  else
+    emit_kernel<false><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
+  return (int)cudaGetLastError();
+}
+
+// Debug surface of SPLIT mode: materialise the sorted 64-bit keys tile << 32 | depth bits, which the
+// production path never needs (compositing reads payload + ranges only).  One warp per tile.
+__global__ void __launch_bounds__(256)
+rebuild_keys_kernel(const uint2* __restrict__ ranges, int tiles, const uint32_t* __restrict__ payload,
+                    const uint32_t* __restrict__ depth_key, uint64_t* __restrict__ keys) {
+  const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (t >= tiles) return;
+  const uint2 rg = ranges[t];
+  for (uint32_t j = rg.x + (threadIdx.x & 31); j < rg.y; j += 32)
+    keys[j] = ((uint64_t)(uint32_t)t << 32) | (uint64_t)depth_key[payload[j]];
+}
+
+int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
+                        uint64_t* keys, cudaStream_t st) {
+  if (tiles <= 0) return 0;
+  rebuild_keys_kernel<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(ranges, tiles, payload, depth_key, keys);
   return (int)cudaGetLastError();
 }
 
@@ -219,6 +278,123 @@ int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k,
   if (k == 0) return 0;
   unsigned blocks = (unsigned)((k + 255) / 256);
   ranges_kernel<<<blocks, 256, 0, st>>>(sorted_keys, k, ranges);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile statistics from the 2-D difference grid written by the projection kernel.
+// One CTA (the grid has (tiles_x+1)*(tiles_y+1) cells: 8 349 at 1080p, 33 k at 4K; it lives in L2).
+//   1. prefix sum along x (one warp per row), 2. prefix sum along y (one thread per column)
+//      -> cell (ty,tx) = number of instances of tile (ty,tx)  [exact: integer arithmetic]
+//   3. exclusive scan over tiles in row-major order -> ranges[t] = (start, start+count), (0,0) if empty
+//   4. histograms of the tile-id digits for the radix passes over the tile field; total K.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatThreads = 1024;
+
+__global__ void __launch_bounds__(kStatThreads)
+tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, int tiles_y,
+                  uint32_t* __restrict__ tile_hist, uint2* __restrict__ ranges, uint32_t* __restrict__ k_total) {
+  extern __shared__ int32_t s_grid[];
+  __shared__ uint32_t s_hist[4][kRadix];
+  __shared__ uint32_t s_warp[kStatThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gw = tiles_x + 1;
+  for (int t = tid; t < 4 * kRadix; t += kStatThreads) (&s_hist[0][0])[t] = 0;
+  // the column pass is a chain of dependent accesses: keep the grid in shared memory whenever it fits
+  int32_t* grid = grid_global;
+  if (use_smem) {
+    const int cells = gw * (tiles_y + 1);
+    for (int t = tid; t < cells; t += kStatThreads) s_grid[t] = grid_global[t];
+    grid = s_grid;
+    __syncthreads();
+  }
+  // 1. rows
+  for (int r = warp; r < tiles_y; r += kStatThreads / 32) {
+    int32_t carry = 0;
+    for (int x0 = 0; x0 < tiles_x; x0 += 32) {
+      const int x = x0 + lane;
+      int32_t v = x < tiles_x ? grid[r * gw + x] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      v += carry;
+      if (x < tiles_x) grid[r * gw + x] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  // 2. columns
+  for (int x = tid; x < tiles_x; x += kStatThreads) {
+    int32_t acc = 0;
+    for (int r = 0; r < tiles_y; ++r) {
+      acc += grid[r * gw + x];
+      grid[r * gw + x] = acc;
+    }
+  }
+  __syncthreads();
+  // 3. exclusive scan in row-major tile order; each thread owns a contiguous chunk of tiles
+  const int tiles = tiles_x * tiles_y;
+  const int per = (tiles + kStatThreads - 1) / kStatThreads;
+  const int t0 = tid * per, t1 = min(t0 + per, tiles);
+  uint32_t local = 0;
+  for (int t = t0; t < t1; ++t) local += (uint32_t)grid[(t / tiles_x) * gw + (t % tiles_x)];
+  uint32_t inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t off = 0, total = 0;
+  for (int w = 0; w < kStatThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < warp) off += t;
+    total += t;
+  }
+  uint32_t run = off + inc - local;
+  // histogram rows: row p counts digit (tile >> 8p) & 255.  A thread's tiles are consecutive, so the
+  // higher digits repeat: accumulate runs locally and issue one shared atomic per run.
+  uint32_t acc[3] = {0, 0, 0};
+  uint32_t cur[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  for (int t = t0; t < t1; ++t) {
+    const uint32_t c = (uint32_t)grid[(t / tiles_x) * gw + (t % tiles_x)];
+    ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+    if (c) {
+      atomicAdd(&s_hist[0][(uint32_t)t & 255u], c);
+#pragma unroll
+      for (int p = 1; p < 4; ++p) {
+        const uint32_t d = ((uint32_t)t >> (8 * p)) & 255u;
+        if (d != cur[p - 1]) {
+          if (acc[p - 1]) atomicAdd(&s_hist[p][cur[p - 1]], acc[p - 1]);
+          cur[p - 1] = d; acc[p - 1] = 0;
+        }
+        acc[p - 1] += c;
+      }
+    }
+    run += c;
+  }
+#pragma unroll
+  for (int p = 1; p < 4; ++p)
+    if (acc[p - 1]) atomicAdd(&s_hist[p][cur[p - 1]], acc[p - 1]);
+  __syncthreads();
+  for (int t = tid; t < 4 * kRadix; t += kStatThreads) tile_hist[t] = (&s_hist[0][0])[t];
+  if (tid == 0) *k_total = total;
+}
+
+int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,
+                      cudaStream_t st) {
+  if (geom.tiles_x <= 0 || geom.tiles_y <= 0) return 0;
+  const size_t bytes = (size_t)(geom.tiles_x + 1) * (size_t)(geom.tiles_y + 1) * sizeof(int32_t);
+  const int use_smem = bytes <= 200 * 1024;
+  if (use_smem && bytes > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(tile_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  tile_stats_kernel<<<1, kStatThreads, use_smem ? bytes : 0, st>>>(diff_grid, use_smem, geom.tiles_x, geom.tiles_y,
+                                                                  tile_hist, ranges, k_total);
   return (int)cudaGetLastError();
 }
 

@@ -295,7 +295,8 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
               const float* __restrict__ conic, const float* __restrict__ min_x, const float* __restrict__ max_x,
               const float* __restrict__ min_y, const float* __restrict__ max_y, const float* __restrict__ opacity,
               FrameGeom geom, int sem, int T, uint32_t* __restrict__ depth_key, float4* __restrict__ rec,
-              float4* __restrict__ bbox, ushort4* __restrict__ rect, uint32_t* __restrict__ count) {
+              float4* __restrict__ bbox, ushort4* __restrict__ rect, uint32_t* __restrict__ count,
+              int32_t* __restrict__ diff_grid) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float mx = means[2 * i], my = means[2 * i + 1];
@@ -336,16 +337,24 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
                 : make_ushort4(0, 0, 0, 0);
   count[i] = cnt;
   depth_key[i] = (uint32_t)i;
+  if (cnt) {  // same 2-D difference grid as the projection kernel (tile_stats_kernel turns it into ranges)
+    const int gw = geom.tiles_x + 1;
+    atomicAdd(&diff_grid[ty0 * gw + tx0], 1);
+    atomicAdd(&diff_grid[ty0 * gw + tx1 + 1], -1);
+    atomicAdd(&diff_grid[(ty1 + 1) * gw + tx0], -1);
+    atomicAdd(&diff_grid[(ty1 + 1) * gw + tx1 + 1], 1);
+  }
 }
 
 int launch_ingest_preprocessed(int64_t m, const float* means, const float* colors, const float* conic,
                                const float* min_x, const float* max_x, const float* min_y, const float* max_y,
                                const float* opacity, FrameGeom geom, const GsbParams& prm, uint32_t* depth_key,
-                               float4* rec, float4* bbox, ushort4* rect, uint32_t* count, cudaStream_t st) {
+                               float4* rec, float4* bbox, ushort4* rect, uint32_t* count, int32_t* diff_grid,
+                               cudaStream_t st) {
   if (m == 0) return 0;
   ingest_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, means, colors, conic, min_x, max_x, min_y, max_y,
                                                             opacity, geom, prm.semantics, prm.tile_size, depth_key,
-                                                            rec, bbox, rect, count);
+                                                            rec, bbox, rect, count, diff_grid);
   return (int)cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@
 // digits first, and every tile instance of a Gaussian shares those digits, so they can be sorted once
 // per Gaussian BEFORE the expansion instead of once per instance after it.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -56,7 +57,24 @@ int ceil_log2(int64_t v) {
   return b < 1 ? 1 : b;
 }
 
-constexpr int kCtlHeaderWords = 16;  // [0] = M counter, [1] = K total
+// control block, zeroed once per frame:
+//   [hdr 16: 0 = M, 1 = K (scan), 2 = K (tile grid)] [hist 8 x 256: rows 0-3 depth digits, 4-7 tile digits]
+//   [difference grid (tiles_x+1)*(tiles_y+1)] [scan look-back status] [depth-sort tickets + status]
+constexpr int kCtlHeaderWords = 16;
+constexpr int kCtlHistWords = kMaxPasses * kRadix;
+
+struct CtlLayout {
+  size_t hist, grid, scan, dsort, total;  // word offsets
+};
+CtlLayout ctl_layout(FrameGeom g, int64_t n_rows, size_t dsort_words) {
+  CtlLayout L;
+  L.hist = kCtlHeaderWords;
+  L.grid = L.hist + kCtlHistWords;
+  L.scan = L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1);
+  L.dsort = L.scan + scan_status_words(n_rows);
+  L.total = L.dsort + dsort_words;
+  return L;
+}
 
 }  // namespace
 
@@ -77,26 +95,34 @@ struct GsbContext {
   bool have_frame = false;
   bool sorted_in_a = true;
   bool emitted_valid = false;
+  bool keys_materialized = true;  // false in SPLIT mode: sorted 64-bit keys are rebuilt on demand (debug)
   bool order_in_a = true;
   bool have_order = false;
   int64_t frame_rows = 0;  // rows of the per-Gaussian arrays of the last frame (N, or M for gsb_render_image)
   GsbFrameInfo info{};
-  cudaEvent_t ev[GSB_NUM_STAGES + 1]{};
-  bool ev_valid[GSB_NUM_STAGES + 1]{};
+  cudaEvent_t ev[GSB_NUM_STAGES + 5]{};
+  int mark_stage[GSB_NUM_STAGES + 5]{};
+  int n_marks = 0;
   float stage_ms[GSB_NUM_STAGES]{};
   bool have_times = false;
 };
 
 namespace {
 
+// chronological list of (stage, event): a stage's time is its event minus the previous one in the list
 struct StageTimer {
   GsbContext* c;
   cudaStream_t st;
   bool on;
-  void mark(int idx) {
-    if (!on) return;
-    cudaEventRecord(c->ev[idx], st);
-    c->ev_valid[idx] = true;
+  void start() {
+    c->n_marks = 0;
+    if (on) cudaEventRecord(c->ev[0], st);
+  }
+  void mark(int stage) {
+    if (!on || c->n_marks >= GSB_NUM_STAGES + 4) return;
+    ++c->n_marks;
+    c->mark_stage[c->n_marks] = stage;
+    cudaEventRecord(c->ev[c->n_marks], st);
   }
 };
 
@@ -110,47 +136,50 @@ int check_params(const GsbCamera* cam, const GsbParams* prm) {
   return GSB_OK;
 }
 
-// depth sort of the per-Gaussian keys (N items): leaves the order in ord_vals_{a|b}
-int depth_sort(GsbContext* c, int64_t n, uint32_t* control_words, cudaStream_t st, int* launches, int* passes) {
+// depth sort of the per-Gaussian keys (N items): leaves the order in ord_vals_{a|b}.  The first pass reads
+// depth_key directly and synthesises payload = index; `hist` = the 4 depth-digit histograms (unweighted).
+int depth_sort(GsbContext* c, int64_t n, const uint32_t* hist, uint32_t* control_words, cudaStream_t st, int* launches,
+               int* passes) {
   GSB_TRY(c->ord_keys_a.ensure((size_t)n * 4));
   GSB_TRY(c->ord_keys_b.ensure((size_t)n * 4));
   GSB_TRY(c->ord_vals_a.ensure((size_t)n * 4));
   GSB_TRY(c->ord_vals_b.ensure((size_t)n * 4));
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->ord_keys_a.p, c->depth_key.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-  GSB_CUDA_TRY((cudaError_t)launch_iota(c->ord_vals_a.as<uint32_t>(), n, st));
-  ++*launches;
   SortPlan plan = make_sort_plan<uint32_t>(n, 0, 32);
   bool in_a = true;
-  GSB_CUDA_TRY((cudaError_t)launch_sort<uint32_t>(plan, c->ord_keys_a.as<uint32_t>(), c->ord_vals_a.as<uint32_t>(),
-                                                  c->ord_keys_b.as<uint32_t>(), c->ord_vals_b.as<uint32_t>(),
-                                                  control_words, &in_a, launches, st));
+  GSB_CUDA_TRY((cudaError_t)launch_sort<uint32_t>(plan, c->depth_key.as<uint32_t>(), nullptr, c->ord_keys_a.as<uint32_t>(),
+                                                  c->ord_vals_a.as<uint32_t>(), c->ord_keys_b.as<uint32_t>(),
+                                                  c->ord_vals_b.as<uint32_t>(), hist, control_words, &in_a, launches, st));
   c->order_in_a = in_a;
   c->have_order = true;
   *passes = plan.passes;
   return GSB_OK;
 }
 
-// everything after the per-Gaussian records exist: scan -> K -> emit -> sort -> ranges.
+// everything after the per-Gaussian records exist: tile stats -> scan -> K -> emit -> sort.
 // `n_rows` per-Gaussian rows; `perm` optional emission order; `low_bits_sorted`: emission order already
 // sorts the low key word (SPLIT mode / pre-sorted rows), so only the tile digits need radix passes.
 int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, FrameGeom geom,
-                 uint32_t* ctl_header, uint32_t* scan_status, cudaStream_t st, StageTimer& tm, int* launches) {
+                 uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches) {
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
   GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
-  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl_header + 1,
-                                        scan_status, st));
+  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl + 1,
+                                        ctl + L.scan, st));
   ++*launches;
-  tm.mark(GSB_STAGE_SCAN + 1);
+  tm.mark(GSB_STAGE_SCAN);
+  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom, ctl + L.hist + 4 * kRadix,
+                                              c->ranges.as<uint2>(), ctl + 2, st));
+  if (tiles > 0) ++*launches;
+  tm.mark(GSB_STAGE_RANGES);
   // the one host round trip of the frame: M and K
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl_header, 8, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 12, cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
   const int64_t m = c->pinned[0], k = c->pinned[1];
-  if (k >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;  // look-back words carry 30-bit counts
+  if (tiles > 0 && (int64_t)c->pinned[2] != k) return GSB_E_INTERNAL;  // scan and tile grid must agree
+  if (k >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;               // look-back words carry 30-bit counts
   c->info.m_in_view = m;
   c->info.k_instances = k;
 
-  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
-  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
-  GSB_CUDA_TRY(cudaMemsetAsync(c->ranges.p, 0, (size_t)(tiles > 0 ? tiles : 1) * 8, st));
   GSB_TRY(c->keys_a.ensure((size_t)k * 8 + 8));
   GSB_TRY(c->keys_b.ensure((size_t)k * 8 + 8));
   GSB_TRY(c->vals_a.ensure((size_t)k * 4 + 4));
@@ -162,23 +191,23 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   GSB_TRY(c->control2.ensure(plan.control_words * 4));
   GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
 
-  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl_header + 1, n_rows, c->depth_key.as<uint32_t>(),
-                                        c->rect.as<ushort4>(), c->count.as<uint32_t>(), geom.tiles_x,
+  plan.keys_only = low_bits_sorted ? 1 : 0;
+  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 1, n_rows, c->depth_key.as<uint32_t>(),
+                                        c->rect.as<ushort4>(), geom.tiles_x, /*combined=*/low_bits_sorted,
                                         c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
   ++*launches;
-  tm.mark(GSB_STAGE_EMIT + 1);
+  tm.mark(GSB_STAGE_EMIT);
   bool in_a = true;
+  const uint32_t* hist = ctl + L.hist + (low_bits_sorted ? 4 * kRadix : 0);
   GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
-                                                  c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(),
+                                                  c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
+                                                  c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(), hist,
                                                   c->control2.as<uint32_t>(), &in_a, launches, st));
+  c->keys_materialized = !low_bits_sorted;
   c->sorted_in_a = in_a;
-  c->emitted_valid = (plan.passes == 1);  // with one pass the a-buffers still hold the emitted order
+  c->emitted_valid = (plan.passes <= 1) && !low_bits_sorted;  // one pass: the a-buffers still hold the emitted order
   c->info.sort_passes = (k > 0) ? plan.passes : 0;
-  tm.mark(GSB_STAGE_SORT + 1);
-  const uint64_t* sk = in_a ? c->keys_a.as<uint64_t>() : c->keys_b.as<uint64_t>();
-  GSB_CUDA_TRY((cudaError_t)launch_ranges(sk, ctl_header + 1, k, c->ranges.as<uint2>(), st));
-  if (k > 0) ++*launches;
-  tm.mark(GSB_STAGE_RANGES + 1);
+  tm.mark(GSB_STAGE_SORT);
   return GSB_OK;
 }
 
@@ -186,13 +215,10 @@ void finish_times(GsbContext* c, cudaStream_t st, bool on) {
   c->have_times = false;
   if (!on) return;
   if (cudaStreamSynchronize(st) != cudaSuccess) return;
-  for (int s = 0; s < GSB_NUM_STAGES; ++s) {
-    c->stage_ms[s] = 0.f;
-    if (!c->ev_valid[s + 1]) continue;
-    int prev = s;  // nearest earlier recorded mark
-    while (prev > 0 && !c->ev_valid[prev]) --prev;
+  for (float& v : c->stage_ms) v = 0.f;
+  for (int i = 1; i <= c->n_marks; ++i) {
     float ms = 0.f;
-    if (c->ev_valid[prev] && cudaEventElapsedTime(&ms, c->ev[prev], c->ev[s + 1]) == cudaSuccess) c->stage_ms[s] = ms;
+    if (cudaEventElapsedTime(&ms, c->ev[i - 1], c->ev[i]) == cudaSuccess) c->stage_ms[c->mark_stage[i]] += ms;
   }
   c->have_times = true;
 }
@@ -213,7 +239,6 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   c->have_order = false;
   std::memset(&c->info, 0, sizeof(c->info));
   c->info.n = n; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
-  for (bool& v : c->ev_valid) v = false;
   StageTimer tm{c, st, prm->collect_stage_times != 0};
 
   const size_t rows = (size_t)(n > 0 ? n : 1);
@@ -222,36 +247,34 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   GSB_TRY(c->rect.ensure(rows * 8));
   GSB_TRY(c->count.ensure(rows * 4));
   SortPlan dplan = make_sort_plan<uint32_t>(n, 0, 32);
-  const size_t scan_words = scan_status_words(n);
-  const size_t ctl_words = kCtlHeaderWords + scan_words + (split ? dplan.control_words : 0);
-  GSB_TRY(c->control.ensure(ctl_words * 4));
-  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, ctl_words * 4, st));
-  uint32_t* hdr = c->control.as<uint32_t>();
-  uint32_t* scan_status = hdr + kCtlHeaderWords;
-  uint32_t* dsort_ctl = scan_status + scan_words;
+  const CtlLayout L = ctl_layout(geom, n, split ? dplan.control_words : 0);
+  GSB_TRY(c->control.ensure(L.total * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
+  uint32_t* ctl = c->control.as<uint32_t>();
 
-  tm.mark(0);
+  tm.start();
   GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, *cam, *prm, geom, c->depth_key.as<uint32_t>(),
-                                           c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), hdr,
-                                           nullptr, st));
+                                           c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), ctl,
+                                           ctl + L.hist, /*hist_weighted=*/split ? 0 : 1,
+                                           reinterpret_cast<int32_t*>(ctl + L.grid), nullptr, st));
   if (n > 0) ++launches;
-  tm.mark(GSB_STAGE_PROJECT + 1);
+  tm.mark(GSB_STAGE_PROJECT);
   const uint32_t* perm = nullptr;
   if (split && n > 0) {
     int dp = 0;
-    GSB_TRY(depth_sort(c, n, dsort_ctl, st, &launches, &dp));
+    GSB_TRY(depth_sort(c, n, ctl + L.hist, ctl + L.dsort, st, &launches, &dp));
     c->info.depth_passes = dp;
     perm = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
-    tm.mark(GSB_STAGE_DEPTH_SORT + 1);
+    tm.mark(GSB_STAGE_DEPTH_SORT);
   }
-  GSB_TRY(bin_and_sort(c, n, perm, split, geom, hdr, scan_status, st, tm, &launches));
+  GSB_TRY(bin_and_sort(c, n, perm, split, geom, ctl, L, st, tm, &launches));
 
   if (!prm->full_cover)  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
     GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
   const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
   GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, *prm, st));
   if (geom.tiles_x * geom.tiles_y > 0) ++launches;
-  tm.mark(GSB_STAGE_COMPOSITE + 1);
+  tm.mark(GSB_STAGE_COMPOSITE);
   c->info.kernel_launches = launches;
   c->frame_rows = n;
   c->have_frame = true;
@@ -275,6 +298,7 @@ const char* gsb_error_string(int s) {
     case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; K < 2^30)";
     case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case GSB_E_ALLOC: return "device memory allocation failed";
+    case GSB_E_INTERNAL: return "internal consistency check failed (scan total != tile-grid total)";
     default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown error";
   }
 }
@@ -305,6 +329,7 @@ int gsb_create(GsbContext** out, int device) {
   GsbContext* c = new (std::nothrow) GsbContext();
   if (!c) return GSB_E_ALLOC;
   c->device = device;
+  if (const char* e = std::getenv("GSB_SORT_ITEMS")) set_sort_items(std::atoi(e));  // tuning knob: 8 (default) or 16
   if (cudaMallocHost((void**)&c->pinned, 64) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }
@@ -428,15 +453,17 @@ int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, in
   GSB_TRY(c->dbg_conic.ensure((size_t)n * 16));
   GSB_TRY(c->dbg_bbox.ensure((size_t)n * 16));
   SortPlan dplan = make_sort_plan<uint32_t>(n, 0, 32);
-  const size_t ctl_words = kCtlHeaderWords + dplan.control_words;
-  GSB_TRY(c->control.ensure(ctl_words * 4));
-  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, ctl_words * 4, st));
+  const CtlLayout L = ctl_layout(geom, n, dplan.control_words);
+  GSB_TRY(c->control.ensure(L.total * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* hdr = c->control.as<uint32_t>();
   DebugOut dbg{c->dbg_cov2d.as<float>(), c->dbg_conic.as<float>(), c->dbg_bbox.as<float>()};
   GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, *cam, *prm, geom, c->depth_key.as<uint32_t>(),
-                                           c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), hdr, &dbg, st));
+                                           c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), hdr,
+                                           hdr + L.hist, /*hist_weighted=*/0, reinterpret_cast<int32_t*>(hdr + L.grid),
+                                           &dbg, st));
   int launches = 1, dp = 0;
-  GSB_TRY(depth_sort(c, n, hdr + kCtlHeaderWords, st, &launches, &dp));
+  GSB_TRY(depth_sort(c, n, hdr + L.hist, hdr + L.dsort, st, &launches, &dp));
   GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, hdr, 4, cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
   const int64_t m = c->pinned[0];
@@ -486,7 +513,6 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   c->have_order = false;
   std::memset(&c->info, 0, sizeof(c->info));
   c->info.n = m; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
-  for (bool& v : c->ev_valid) v = false;
   StageTimer tm{c, st, prm.collect_stage_times != 0};
   int launches = 0;
 
@@ -512,18 +538,18 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   GSB_TRY(c->rect.ensure(rows * 8));
   GSB_TRY(c->count.ensure(rows * 4));
   GSB_TRY(c->bbox.ensure(rows * 16));
-  const size_t scan_words = scan_status_words(m);
-  const size_t ctl_words = kCtlHeaderWords + scan_words;
-  GSB_TRY(c->control.ensure(ctl_words * 4));
-  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, ctl_words * 4, st));
+  const CtlLayout L = ctl_layout(geom, m, 0);
+  GSB_TRY(c->control.ensure(L.total * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* hdr = c->control.as<uint32_t>();
-  tm.mark(0);
+  tm.start();
   GSB_CUDA_TRY((cudaError_t)launch_ingest_preprocessed(m, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], geom,
                                                        prm, c->depth_key.as<uint32_t>(), c->rec.as<float4>(),
-                                                       c->bbox.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), st));
+                                                       c->bbox.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(),
+                                                       reinterpret_cast<int32_t*>(hdr + L.grid), st));
   if (m > 0) ++launches;
-  tm.mark(GSB_STAGE_PROJECT + 1);
-  GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, geom, hdr, hdr + kCtlHeaderWords, st, tm, &launches));
+  tm.mark(GSB_STAGE_PROJECT);
+  GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, geom, hdr, L, st, tm, &launches));
   c->info.m_in_view = m;
 
   float* dev_image = out_image;
@@ -538,7 +564,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   else
     GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, prm, st));
   if (geom.tiles_x * geom.tiles_y > 0) ++launches;
-  tm.mark(GSB_STAGE_COMPOSITE + 1);
+  tm.mark(GSB_STAGE_COMPOSITE);
   if (host_out) GSB_CUDA_TRY(cudaMemcpyAsync(out_image, dev_image, bytes, cudaMemcpyDeviceToHost, st));
   c->info.kernel_launches = launches;
   c->frame_rows = m;
@@ -611,8 +637,19 @@ int gsb_debug_sorted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   const size_t k = (size_t)c->info.k_instances;
   if (k == 0) return GSB_OK;
-  if (keys) GSB_CUDA_TRY(cudaMemcpy(keys, c->sorted_in_a ? c->keys_a.p : c->keys_b.p, k * 8, cudaMemcpyDefault));
-  if (payload) GSB_CUDA_TRY(cudaMemcpy(payload, c->sorted_in_a ? c->vals_a.p : c->vals_b.p, k * 4, cudaMemcpyDefault));
+  const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
+  if (keys) {
+    if (c->keys_materialized) {
+      GSB_CUDA_TRY(cudaMemcpy(keys, c->sorted_in_a ? c->keys_a.p : c->keys_b.p, k * 8, cudaMemcpyDefault));
+    } else {
+      // SPLIT mode moved only (tile | index) through the tile passes: rebuild tile<<32 | depth bits
+      GSB_TRY(c->scratch.ensure(k * 8));
+      GSB_CUDA_TRY((cudaError_t)launch_rebuild_keys(c->ranges.as<uint2>(), c->info.tiles_x * c->info.tiles_y, sv,
+                                                    c->depth_key.as<uint32_t>(), c->scratch.as<uint64_t>(), 0));
+      GSB_CUDA_TRY(cudaMemcpy(keys, c->scratch.p, k * 8, cudaMemcpyDefault));
+    }
+  }
+  if (payload) GSB_CUDA_TRY(cudaMemcpy(payload, sv, k * 4, cudaMemcpyDefault));
   return GSB_OK;
 }
 
@@ -654,12 +691,15 @@ int gsb_sort_pairs_u64(GsbContext* c, int64_t n, uint64_t* keys_in, uint32_t* va
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   if (n == 0) return GSB_OK;
   SortPlan plan = make_sort_plan<uint64_t>(n, begin_bit, end_bit);
-  GSB_TRY(c->control2.ensure(plan.control_words * 4));
-  GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+  const size_t words = (size_t)kCtlHistWords + plan.control_words;
+  GSB_TRY(c->control2.ensure(words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, words * 4, st));
+  uint32_t* hist = c->control2.as<uint32_t>();
+  GSB_CUDA_TRY((cudaError_t)launch_key_histogram<uint64_t>(plan, keys_in, hist, st));
   bool in_a = true;
   int launches = 0;
-  GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, keys_in, vals_in, keys_out, vals_out, c->control2.as<uint32_t>(),
-                                                  &in_a, &launches, st));
+  GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, keys_in, vals_in, keys_in, vals_in, keys_out, vals_out, hist,
+                                                  hist + kCtlHistWords, &in_a, &launches, st));
   if (in_a) {  // even number of passes (or none): result sits in the input buffers
     GSB_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     GSB_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));

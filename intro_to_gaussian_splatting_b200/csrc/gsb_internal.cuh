@@ -57,9 +57,17 @@ struct DebugOut {
 int launch_repack(const float* xyz, const float* scales, const float* quats, const float* colors,
                   const float* opacity, float* planes, int64_t n, int64_t n_pad, cudaStream_t st);
 
+// depth_hist: 4*256 zeroed words (digit histograms of the depth keys; weighted by tile count when
+// hist_weighted).  diff_grid: (tiles_x+1)*(tiles_y+1) zeroed ints (2-D difference grid of the tile rects).
 int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
                    FrameGeom geom, uint32_t* depth_key, float4* rec, ushort4* rect, uint32_t* count,
-                   uint32_t* m_counter, const DebugOut* dbg, cudaStream_t st);
+                   uint32_t* m_counter, uint32_t* depth_hist, int hist_weighted, int32_t* diff_grid,
+                   const DebugOut* dbg, cudaStream_t st);
+
+// 2-D prefix sum of the difference grid (in place) -> instances per tile -> per-tile [start,end) ranges
+// (empty tiles (0,0)), histograms of the tile-id digits (tile_hist: 4*256 zeroed words), total K.
+int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,
+                      cudaStream_t st);
 
 // exclusive scan of count[perm ? perm[i] : i] for i < n  -> offsets[i]; total -> *total.
 // `status` needs scan_status_words(n) zeroed u32 words.
@@ -67,25 +75,37 @@ size_t scan_status_words(int64_t n);
 int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* total,
                 uint32_t* status, cudaStream_t st);
 
+// combined = false: keys = tile<<32 | depth bits, payload = Gaussian index (FULL mode);
+// combined = true:  keys = tile<<32 | Gaussian index, payload untouched (SPLIT mode, keys-only tile passes)
 int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
-                const uint32_t* depth_key, const ushort4* rect, const uint32_t* count, int tiles_x,
-                uint64_t* keys, uint32_t* payload, cudaStream_t st);
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
+                uint32_t* payload, cudaStream_t st);
+// debug only: sorted keys tile<<32 | depth bits from ranges + sorted payload (SPLIT mode never stores them)
+int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
+                        uint64_t* keys, cudaStream_t st);
 
 // ---- onesweep radix sort ----
 struct SortPlan {
   int begin_bit, end_bit, passes;
+  int items;              // keys per thread (8 or 16)
+  int keys_only;          // 1: payload packed in unsorted key bits; last pass writes low 32 bits to vals
   int64_t n;
   int64_t tiles;          // onesweep tiles per pass
-  size_t control_words;   // u32 words of control memory (histograms + tickets + look-back status)
+  size_t control_words;   // u32 words of control memory (tickets + look-back status), zeroed by the caller
 };
+void set_sort_items(int items);
 template <typename KeyT>
 SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit);
-// Sorts (keys_a, vals_a) using (keys_b, vals_b) as the alternate buffer.  Returns in *result_in_a
-// whether the sorted data ended in the a-buffers (even number of passes).  `control` must hold
-// plan.control_words zeroed u32 words.
+// digit histograms computed from the keys (stand-alone sort only); hist = kMaxPasses*256 zeroed words
 template <typename KeyT>
-int launch_sort(const SortPlan& plan, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                uint32_t* control, bool* result_in_a, int* launches, cudaStream_t st);
+int launch_key_histogram(const SortPlan& plan, const KeyT* keys, uint32_t* hist, cudaStream_t st);
+// Pass 0 reads (keys_src, vals_src) -- vals_src == nullptr means "payload = index" -- and writes the
+// b-buffers; later passes ping-pong b -> a -> b.  keys_src may be keys_a itself.  hist: [passes][256]
+// digit histograms of the keys.  *result_in_a: sorted data ended in the a-buffers (even pass count).
+template <typename KeyT>
+int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals_src, KeyT* keys_a, uint32_t* vals_a,
+                KeyT* keys_b, uint32_t* vals_b, const uint32_t* hist, uint32_t* control, bool* result_in_a,
+                int* launches, cudaStream_t st);
 
 int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k, uint2* ranges, cudaStream_t st);
 
@@ -105,7 +125,8 @@ int launch_iota(uint32_t* p, int64_t n, cudaStream_t st);
 int launch_ingest_preprocessed(int64_t m, const float* means, const float* colors, const float* conic,
                                const float* min_x, const float* max_x, const float* min_y, const float* max_y,
                                const float* opacity, FrameGeom geom, const GsbParams& prm, uint32_t* depth_key,
-                               float4* rec, float4* bbox, ushort4* rect, uint32_t* count, cudaStream_t st);
+                               float4* rec, float4* bbox, ushort4* rect, uint32_t* count, int32_t* diff_grid,
+                               cudaStream_t st);
 int launch_composite_cu(const uint2* ranges, const uint32_t* payload, const float4* rec, const float4* bbox,
                         float* image, FrameGeom geom, const GsbParams& prm, cudaStream_t st);
 

@@ -26,8 +26,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = 16;
-constexpr int kSortTile = kThreads * kItems;  // 4096 keys per CTA
+constexpr int kLookBatch = 8;   // look-back loads in flight per lane
+constexpr int kHistItems = 16;
+constexpr int kSortTile = kThreads * kHistItems;  // keys per histogram chunk
 
 constexpr uint32_t kFlagShift = 30;
 constexpr uint32_t kFlagAggregate = 1u << kFlagShift;
@@ -60,7 +61,7 @@ histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int begin_bit, int en
   const int64_t per_block = (int64_t)kSortTile;
   for (int64_t base = (int64_t)blockIdx.x * per_block; base < n; base += (int64_t)gridDim.x * per_block) {
 #pragma unroll 4
-    for (int it = 0; it < kItems; ++it) {
+    for (int it = 0; it < kHistItems; ++it) {
       const int64_t i = base + (int64_t)it * kThreads + threadIdx.x;
       const bool ok = i < n;
       const KeyT k = ok ? keys[i] : (KeyT)0;
@@ -83,15 +84,36 @@ histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int begin_bit, int en
 }
 
 // ---- one digit pass ------------------------------------------------------------------------------
+// kMode: what travels with the key
+//   kPairs            (key, u32 payload) pairs; vals_in == nullptr means "payload = the key's index"
+//                     (first pass of the per-Gaussian depth sort: saves an iota kernel and a key copy)
+//   kKeysOnly         the payload is packed into key bits that are not being sorted (tile<<32 | gaussian)
+//   kKeysOnlyLowOut   same, and only the low 32 bits of each key are written (to vals_out): the last tile
+//                     pass of SPLIT mode, after which nothing reads the tile half of the key any more
+enum SortMode { kPairs = 0, kKeysOnly = 1, kKeysOnlyLowOut = 2 };
+
+__device__ __forceinline__ uint32_t digit32(uint32_t k, int shift, uint32_t mask) { return (k >> shift) & mask; }
+__device__ __forceinline__ uint32_t digit64(uint64_t k, int shift, uint32_t mask) {
+  const uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
+  const uint32_t v = shift >= 32 ? (hi >> (shift - 32)) : __funnelshift_r(lo, hi, shift);  // warp-uniform branch
+  return v & mask;
+}
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ uint32_t digit_fast(KeyT k, int shift, uint32_t mask) {
+  if constexpr (sizeof(KeyT) == 8) return digit64((uint64_t)k, shift, mask);
+  else return digit32((uint32_t)k, shift, mask);
+}
+
+template <typename KeyT, int kItems, int kMode>
+__global__ void __launch_bounds__(kThreads, kItems == 8 ? 3 : 2)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                 const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
-                uint32_t* status /* [tiles][256] */) {
+                uint32_t* status /* [num_tiles][256] */) {
+  constexpr int kTileKeys = kThreads * kItems;
   __shared__ union {
-    KeyT keys[kSortTile];
-    uint32_t vals[kSortTile];
+    KeyT keys[kTileKeys];
+    uint32_t vals[kTileKeys];
   } exch;
   __shared__ uint32_t s_cnt[kWarps][kRadix];
   __shared__ uint32_t s_tile_start[kRadix];
@@ -104,46 +126,52 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   for (int i = tid; i < kWarps * kRadix; i += kThreads) (&s_cnt[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
-  const int64_t base = (int64_t)tile * kSortTile;
-  const int valid = (int)min((int64_t)kSortTile, n - base);
+  const int64_t base = (int64_t)tile * kTileKeys;
+  const int valid = (int)min((int64_t)kTileKeys, n - base);
+  const bool full = valid == kTileKeys;  // all tiles but the last: no bounds checks
   const uint32_t mask = (1u << bits) - 1u;
   const KeyT kPad = ~(KeyT)0;
 
-  // 2. warp-striped coalesced loads; payload prefetched alongside
+  // 2. warp-striped coalesced loads
   KeyT key[kItems];
-  uint32_t val[kItems];
   const int64_t wbase = base + (int64_t)warp * (32 * kItems) + lane;
+  if (full) {
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    const int64_t idx = wbase + i * 32;
-    key[i] = idx < n ? keys_in[idx] : kPad;
-  }
+    for (int i = 0; i < kItems; ++i) key[i] = keys_in[wbase + i * 32];
+  } else {
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    const int64_t idx = wbase + i * 32;
-    val[i] = idx < n ? vals_in[idx] : 0u;
+    for (int i = 0; i < kItems; ++i) {
+      const int64_t idx = wbase + i * 32;
+      key[i] = idx < n ? keys_in[idx] : kPad;
+    }
   }
 
-  // 3. stable ranks inside the warp
+  // 3. stable ranks inside the warp, written for instruction-level parallelism: all matches first, then all
+  //    shared-memory atomics (leaders only; an ATOMS returns the running count, and shared atomics of one
+  //    warp retire in issue order, which is what keeps equal digits in item order), then all broadcasts.
+  uint32_t info[kItems];  // leader | rank among peers << 8 | peers << 16
   uint32_t pos[kItems];
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
-    const uint32_t d = digit_of(key[i], shift, mask);
+    const uint32_t d = digit_fast(key[i], shift, mask);
     const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (lane == leader) {
-      old = s_cnt[warp][d];
-      s_cnt[warp][d] = old + (uint32_t)__popc(peers);
-    }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    pos[i] = old + (uint32_t)__popc(peers & lt_mask);
-    __syncwarp();
+    info[i] = (uint32_t)(__ffs(peers) - 1) | ((uint32_t)__popc(peers & lt_mask) << 8) | ((uint32_t)__popc(peers) << 16);
   }
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    pos[i] = 0;
+    if (((info[i] >> 8) & 255u) == 0u)  // rank 0 among its peers == the leader
+      pos[i] = atomicAdd(&s_cnt[warp][digit_fast(key[i], shift, mask)], info[i] >> 16);
+  }
+#pragma unroll
+  for (int i = 0; i < kItems; ++i)
+    pos[i] = __shfl_sync(0xffffffffu, pos[i], (int)(info[i] & 31u)) + ((info[i] >> 8) & 255u);
   __syncthreads();
 
-  // 4. thread d owns digit d
+  // 4a. thread d owns digit d: scan the warp counters, publish the tile's aggregate as early as possible
+  uint32_t real, tile_start, bin_base;
+  uint32_t* st = status + (size_t)tile * kRadix + tid;
   {
     const int d = tid;
     uint32_t sum = 0;
@@ -154,8 +182,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
       sum += t;
     }
     // padding keys (all ones) sit in the highest used bin and, being last in tile order, last in it
-    uint32_t real = sum;
-    if ((uint32_t)d == mask) real -= (uint32_t)(kSortTile - valid);
+    real = sum;
+    if ((uint32_t)d == mask) real -= (uint32_t)(kTileKeys - valid);
+    st_relaxed(st, (tile == 0 ? kFlagPrefix : kFlagAggregate) | real);
 
     // block-wide exclusive scans: local tile counts (-> smem layout) and the global histogram (-> bin bases)
     uint32_t a = sum, b = hist[d];
@@ -172,63 +201,102 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 #pragma unroll
     for (int w = 0; w < kWarps; ++w)
       if (w < warp) { wa += s_scan[0][w]; wb += s_scan[1][w]; }
-    const uint32_t tile_start = wa + a - a_in;
-    const uint32_t bin_base = wb + b - b_in;
-
-    // decoupled look-back over earlier tiles for this digit
-    uint32_t excl = 0;
-    uint32_t* st = status + (size_t)tile * kRadix + d;
-    if (tile == 0) {
-      st_relaxed(st, kFlagPrefix | real);
-    } else {
-      st_relaxed(st, kFlagAggregate | real);
-      const uint32_t* q = st - kRadix;
-      for (uint32_t t = tile; t > 0; --t, q -= kRadix) {
-        uint32_t s = ld_relaxed(q);
-        while ((s >> kFlagShift) == 0) s = ld_relaxed(q);
-        excl += s & kValueMask;
-        if ((s >> kFlagShift) == 2u) break;
-      }
-      st_relaxed(st, kFlagPrefix | ((excl + real) & kValueMask));
-    }
+    tile_start = wa + a - a_in;
+    bin_base = wb + b - b_in;
     s_tile_start[d] = tile_start;
-    s_gofs[d] = bin_base + excl - tile_start;  // global index = s_gofs[d] + local position (mod 2^32)
   }
   __syncthreads();
 
-  // 5a. keys -> smem in locally sorted order
+  // 5a. keys -> smem in locally sorted order (gives earlier tiles time to publish before the look-back)
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
-    const uint32_t d = digit_of(key[i], shift, mask);
+    const uint32_t d = digit_fast(key[i], shift, mask);
     pos[i] += s_tile_start[d] + s_cnt[warp][d];
     exch.keys[pos[i]] = key[i];
   }
+
+  // 4b. decoupled look-back for this thread's digit.  Predecessor words are fetched in BATCHES of
+  //     independent loads (2 first -- in steady state the nearest tiles already hold an inclusive prefix --
+  //     then 8 at a time): at the start of a pass several hundred tiles are in flight with only their
+  //     aggregates published, and a one-at-a-time walk pays one L2 round trip for each of them.
+  {
+    uint32_t excl = 0;
+    if (tile != 0) {
+      const uint32_t* col = status + tid;  // status is [tile][256]
+      int64_t t = (int64_t)tile - 1;
+      bool found = false;
+      {
+        uint32_t v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t)(t - k) * kRadix) : kFlagPrefix;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (found) break;
+          uint32_t x = v[k];
+          while ((x >> kFlagShift) == 0) x = ld_relaxed(col + (size_t)(t - k) * kRadix);
+          excl += x & kValueMask;
+          found = (x >> kFlagShift) == 2u;
+        }
+        t -= 2;
+      }
+      while (!found) {
+        uint32_t v[kLookBatch];
+#pragma unroll
+        for (int k = 0; k < kLookBatch; ++k)
+          v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t)(t - k) * kRadix) : kFlagPrefix;
+#pragma unroll
+        for (int k = 0; k < kLookBatch; ++k) {
+          if (found) break;
+          uint32_t x = v[k];
+          while ((x >> kFlagShift) == 0) x = ld_relaxed(col + (size_t)(t - k) * kRadix);
+          excl += x & kValueMask;
+          found = (x >> kFlagShift) == 2u;
+        }
+        t -= kLookBatch;
+      }
+      st_relaxed(st, kFlagPrefix | ((excl + real) & kValueMask));
+    }
+    s_gofs[tid] = bin_base + excl - tile_start;  // global index = s_gofs[d] + local position (mod 2^32)
+  }
   __syncthreads();
+
   // 5b. keys -> global: consecutive threads write consecutive addresses inside each digit run
   uint32_t dst[kItems];
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const int j = tid + i * kThreads;
     dst[i] = 0;
-    if (j < valid) {
+    if (full || j < valid) {
       const KeyT k = exch.keys[j];
-      dst[i] = s_gofs[digit_of(k, shift, mask)] + (uint32_t)j;
-      keys_out[dst[i]] = k;
+      dst[i] = s_gofs[digit_fast(k, shift, mask)] + (uint32_t)j;
+      if constexpr (kMode == kKeysOnlyLowOut) vals_out[dst[i]] = (uint32_t)k;
+      else keys_out[dst[i]] = k;
     }
   }
-  __syncthreads();
-  // 5c. payload by the same route
+  if constexpr (kMode == kPairs) {
+    // 5c. payload by the same route (loaded late: keeps the register footprint of the ranking phase small)
+    uint32_t val[kItems];
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) exch.vals[pos[i]] = val[i];
-  __syncthreads();
+    for (int i = 0; i < kItems; ++i) {
+      const int64_t idx = wbase + i * 32;
+      val[i] = vals_in ? ((full || idx < n) ? vals_in[idx] : 0u) : (uint32_t)idx;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    const int j = tid + i * kThreads;
-    if (j < valid) vals_out[dst[i]] = exch.vals[j];
+    for (int i = 0; i < kItems; ++i) exch.vals[pos[i]] = val[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const int j = tid + i * kThreads;
+      if (full || j < valid) vals_out[dst[i]] = exch.vals[j];
+    }
   }
 }
 
 }  // namespace
+
+static int g_sort_items = 8;  // keys per thread of the onesweep tile (8 or 16); tuning knob, see gsb_api.cu
+void set_sort_items(int items) { g_sort_items = (items == 16) ? 16 : 8; }
 
 template <typename KeyT>
 SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
@@ -238,41 +306,77 @@ SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
   p.passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
   if (p.passes < 0) p.passes = 0;
   p.n = n;
-  p.tiles = (n + kSortTile - 1) / kSortTile;
-  // [hist: passes*256][tickets: 8][status: passes * tiles * 256]
-  p.control_words = (size_t)kMaxPasses * kRadix + 8 + (size_t)p.passes * (size_t)p.tiles * kRadix;
+  p.keys_only = 0;
+  p.items = g_sort_items;
+  const int64_t tile_keys = (int64_t)kThreads * p.items;
+  p.tiles = (n + tile_keys - 1) / tile_keys;
+  // [tickets: 8][status: passes * tiles * 256]
+  p.control_words = 8 + (size_t)p.passes * (size_t)p.tiles * kRadix;
   return p;
 }
 template SortPlan make_sort_plan<uint32_t>(int64_t, int, int);
 template SortPlan make_sort_plan<uint64_t>(int64_t, int, int);
 
+// Histogram of the keys themselves (only the stand-alone sort entry needs it; the frame pipeline gets its
+// histograms from the projection kernel and tile_stats_kernel).  hist: kMaxPasses*256 zeroed words.
 template <typename KeyT>
-int launch_sort(const SortPlan& plan, KeyT* keys_a, uint32_t* vals_a, KeyT* keys_b, uint32_t* vals_b,
-                uint32_t* control, bool* result_in_a, int* launches, cudaStream_t st) {
+int launch_key_histogram(const SortPlan& plan, const KeyT* keys, uint32_t* hist, cudaStream_t st) {
+  if (plan.n == 0 || plan.passes == 0) return 0;
+  int64_t chunks = (plan.n + kSortTile - 1) / kSortTile;
+  int hist_blocks = chunks < 148 * 4 ? (int)chunks : 148 * 4;
+  histogram_kernel<KeyT><<<hist_blocks, kThreads, 0, st>>>(keys, plan.n, plan.begin_bit, plan.end_bit, plan.passes, hist);
+  return (int)cudaGetLastError();
+}
+template int launch_key_histogram<uint32_t>(const SortPlan&, const uint32_t*, uint32_t*, cudaStream_t);
+template int launch_key_histogram<uint64_t>(const SortPlan&, const uint64_t*, uint32_t*, cudaStream_t);
+
+template <typename KeyT, int kItems>
+static void launch_pass(int mode, unsigned tiles, cudaStream_t st, const KeyT* kin, const uint32_t* vin, KeyT* kout,
+                        uint32_t* vout, int64_t n, int shift, int bits, const uint32_t* hist, uint32_t* ticket,
+                        uint32_t* status) {
+  if (mode == kPairs)
+    onesweep_kernel<KeyT, kItems, kPairs><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+  else if (mode == kKeysOnly)
+    onesweep_kernel<KeyT, kItems, kKeysOnly><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+  else
+    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+}
+
+template <typename KeyT>
+int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals_src, KeyT* keys_a, uint32_t* vals_a,
+                KeyT* keys_b, uint32_t* vals_b, const uint32_t* hist, uint32_t* control, bool* result_in_a,
+                int* launches, cudaStream_t st) {
+  // pass 0 reads (keys_src, vals_src) and writes the b-buffers; later passes ping-pong b -> a -> b ...
+  // keys_src may alias keys_a (in-place use) or be a read-only array that must survive (depth keys).
+  // plan.keys_only: no payload arrays; the LAST pass writes only the low 32 bits of each key into the
+  // vals buffer of its destination side (vals_a or vals_b).
   *result_in_a = true;
   if (plan.n == 0 || plan.passes == 0) return 0;
-  uint32_t* hist = control;
-  uint32_t* tickets = control + (size_t)kMaxPasses * kRadix;
-  uint32_t* status = tickets + 8;
-  int hist_blocks = plan.tiles < 148 * 4 ? (int)plan.tiles : 148 * 4;
-  histogram_kernel<KeyT><<<hist_blocks, kThreads, 0, st>>>(keys_a, plan.n, plan.begin_bit, plan.end_bit, plan.passes, hist);
-  if (launches) ++*launches;
-  KeyT* kin = keys_a; KeyT* kout = keys_b;
-  uint32_t* vin = vals_a; uint32_t* vout = vals_b;
+  uint32_t* tickets = control;
+  uint32_t* status = control + 8;
+  const KeyT* kin = keys_src; const uint32_t* vin = vals_src;
+  KeyT* kout = keys_b; uint32_t* vout = vals_b;
   for (int p = 0; p < plan.passes; ++p) {
     const int shift = plan.begin_bit + p * kRadixBits;
     const int bits = (plan.end_bit - shift) < kRadixBits ? (plan.end_bit - shift) : kRadixBits;
-    onesweep_kernel<KeyT><<<(unsigned)plan.tiles, kThreads, 0, st>>>(
-        kin, vin, kout, vout, plan.n, shift, bits, hist + (size_t)p * kRadix, tickets + p,
-        status + (size_t)p * (size_t)plan.tiles * kRadix);
+    uint32_t* stp = status + (size_t)p * (size_t)plan.tiles * kRadix;
+    const int mode = !plan.keys_only ? kPairs : (p == plan.passes - 1 ? kKeysOnlyLowOut : kKeysOnly);
+    if (plan.items == 16)
+      launch_pass<KeyT, 16>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits,
+                            hist + (size_t)p * kRadix, tickets + p, stp);
+    else
+      launch_pass<KeyT, 8>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits,
+                           hist + (size_t)p * kRadix, tickets + p, stp);
     if (launches) ++*launches;
-    KeyT* tk = kin; kin = kout; kout = tk;
-    uint32_t* tv = vin; vin = vout; vout = tv;
+    kin = kout; vin = vout;
+    if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }
   }
   *result_in_a = (plan.passes % 2) == 0;
   return (int)cudaGetLastError();
 }
-template int launch_sort<uint32_t>(const SortPlan&, uint32_t*, uint32_t*, uint32_t*, uint32_t*, uint32_t*, bool*, int*, cudaStream_t);
-template int launch_sort<uint64_t>(const SortPlan&, uint64_t*, uint32_t*, uint64_t*, uint32_t*, uint32_t*, bool*, int*, cudaStream_t);
+template int launch_sort<uint32_t>(const SortPlan&, const uint32_t*, const uint32_t*, uint32_t*, uint32_t*, uint32_t*,
+                                   uint32_t*, const uint32_t*, uint32_t*, bool*, int*, cudaStream_t);
+template int launch_sort<uint64_t>(const SortPlan&, const uint64_t*, const uint32_t*, uint64_t*, uint32_t*, uint64_t*,
+                                   uint32_t*, const uint32_t*, uint32_t*, bool*, int*, cudaStream_t);
 
 }  // namespace gsb

@@ -110,20 +110,38 @@ __device__ __forceinline__ void tile_interval(float mn, float mx, int T, int nti
   hi = h > ntiles - 1 ? ntiles - 1 : h;
 }
 
+// Besides the per-Gaussian records the kernel accumulates everything the radix sort needs to know
+// about the keys WITHOUT ever reading them back:
+//   * histograms of the four depth-key digits (block-private in shared memory, flushed with one RED
+//     per non-empty bin per block): unweighted over all N rows for the per-Gaussian depth sort of SPLIT
+//     mode, or weighted by the tile count for the 64-bit key sort of FULL mode;
+//   * a 2-D difference grid of the tile rects (+1,-1,-1,+1 at the rect corners, 4 REDs per Gaussian);
+//     its 2-D prefix sum (tile_stats_kernel) is the exact number of instances per tile, which yields
+//     the tile-digit histograms, the per-tile [start,end) ranges and K.
+// The grid is persistent (a multiple of the SM count) so that the histogram flush stays small.
 template <bool kDebug>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const __grid_constant__ ProjectArgs a,
                uint32_t* __restrict__ depth_key, float4* __restrict__ rec, ushort4* __restrict__ rect,
-               uint32_t* __restrict__ count, uint32_t* __restrict__ m_counter, DebugOut dbg) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
-  if (i < n) {
+               uint32_t* __restrict__ count, uint32_t* __restrict__ m_counter, uint32_t* __restrict__ depth_hist,
+               int hist_weighted, int32_t* __restrict__ diff_grid, DebugOut dbg) {
+  __shared__ uint32_t s_hist[4][kRadix];
+  __shared__ int s_cnt;
+  for (int t = threadIdx.x; t < 4 * kRadix; t += blockDim.x) (&s_hist[0][0])[t] = 0;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int gw = a.tiles_x + 1;  // width of the difference grid
+  int kept = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bool keep = false;
+    uint32_t cnt = 0;
+    uint32_t dkey = 0xFFFFFFFFu;
+    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
     const float x = planes[PX * n_pad + i], y = planes[PY * n_pad + i], z = planes[PZ * n_pad + i];
     const float* V = a.cam.world2view;
     const float* F = a.cam.full_proj;
     const float vz = rowvec_col(x, y, z, V, 2);
     keep = vz >= a.minimum_z;  // in_view_frustum; the ONLY cull (no x/y frustum test in the reference)
-    uint32_t cnt = 0;
     if (keep) {
       // issue the remaining loads early so they overlap the arithmetic below
       const float sx = planes[PSX * n_pad + i], sy = planes[PSY * n_pad + i], sz = planes[PSZ * n_pad + i];
@@ -225,7 +243,6 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       const float mnx = floorf(__fsub_rn(px, rad)), mny = floorf(__fsub_rn(py, rad));
       const float mxx = ceilf(__fadd_rn(px, rad)), mxy = ceilf(__fadd_rn(py, rad));
 
-      int tx0, tx1, ty0, ty1;
       tile_interval(mnx, mxx, a.tile_size, a.tiles_x, tx0, tx1);
       tile_interval(mny, mxy, a.tile_size, a.tiles_y, ty0, ty1);
       if (tx1 >= tx0 && ty1 >= ty0) cnt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
@@ -238,42 +255,62 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, op2, cr);
       rec[3 * i + 2] = make_float4(cg, cb, rad, sig1);
       rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
-      depth_key[i] = __float_as_uint(vz);
+      dkey = __float_as_uint(vz);
       if (kDebug) {
         reinterpret_cast<float4*>(dbg.cov2d)[i] = make_float4(ca, cbb, cc, cd);
         reinterpret_cast<float4*>(dbg.conic)[i] = make_float4(i00, i01, i10, i11);
         reinterpret_cast<float4*>(dbg.bbox)[i] = make_float4(mnx, mny, mxx, mxy);
       }
     } else {
-      depth_key[i] = 0xFFFFFFFFu;  // sorts behind every real depth (z >= 0.2 > 0, finite)
       rect[i] = make_ushort4(0, 0, 0, 0);
     }
     count[i] = cnt;
+    depth_key[i] = dkey;  // 0xFFFFFFFF when culled: sorts behind every real depth (z >= 0.2 > 0, finite)
+    kept += keep ? 1 : 0;
+    const uint32_t w = hist_weighted ? cnt : 1u;
+    if (w) {
+      atomicAdd(&s_hist[0][dkey & 255u], w);
+      atomicAdd(&s_hist[1][(dkey >> 8) & 255u], w);
+      atomicAdd(&s_hist[2][(dkey >> 16) & 255u], w);
+      atomicAdd(&s_hist[3][dkey >> 24], w);
+    }
+    if (cnt) {
+      atomicAdd(&diff_grid[ty0 * gw + tx0], 1);
+      atomicAdd(&diff_grid[ty0 * gw + tx1 + 1], -1);
+      atomicAdd(&diff_grid[(ty1 + 1) * gw + tx0], -1);
+      atomicAdd(&diff_grid[(ty1 + 1) * gw + tx1 + 1], 1);
+    }
   }
   // M = number of in-view Gaussians: one atomic per block
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-  unsigned b = __ballot_sync(0xffffffffu, keep);
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_cnt, __popc(b));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&s_cnt, kept);
   __syncthreads();
   if (threadIdx.x == 0 && s_cnt) atomicAdd(m_counter, (uint32_t)s_cnt);
+  for (int t = threadIdx.x; t < 4 * kRadix; t += blockDim.x) {
+    const uint32_t v = (&s_hist[0][0])[t];
+    if (v) atomicAdd(&depth_hist[t], v);
+  }
 }
 
 int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
                    FrameGeom geom, uint32_t* depth_key, float4* rec, ushort4* rect, uint32_t* count,
-                   uint32_t* m_counter, const DebugOut* dbg, cudaStream_t st) {
+                   uint32_t* m_counter, uint32_t* depth_hist, int hist_weighted, int32_t* diff_grid,
+                   const DebugOut* dbg, cudaStream_t st) {
   if (n == 0) return 0;
   ProjectArgs a;
   a.cam = cam;
   a.minimum_z = prm.minimum_z; a.fov_clamp = prm.fov_clamp; a.det_min = prm.det_min;
   a.lambda_floor = prm.lambda_floor; a.sigma_extent = prm.sigma_extent;
   a.tile_size = prm.tile_size; a.tiles_x = geom.tiles_x; a.tiles_y = geom.tiles_y;
-  unsigned blocks = (unsigned)((n + 255) / 256);
+  int64_t want = (n + 255) / 256;
+  unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);  // persistent: 8 CTAs per SM
   if (dbg)
-    project_kernel<true><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, *dbg);
+    project_kernel<true><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, depth_hist,
+                                                 hist_weighted, diff_grid, *dbg);
   else
-    project_kernel<false><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, DebugOut{});
+    project_kernel<false><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, depth_hist,
+                                                  hist_weighted, diff_grid, DebugOut{});
   return (int)cudaGetLastError();
 }
 
