@@ -80,7 +80,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="gsb_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -188,18 +188,27 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def stage_bytes(info, n, width, height, split):
-    """Algorithmic HBM bytes per frame and stage."""
+    """Algorithmic HBM bytes per frame and stage.  N Gaussians, M in view, K tile
+    instances, P pixels.  SPLIT: the tile passes move one u64 (tile<<32 | index) per instance and the last
+    pass writes only the 4-byte index."""
     N, M, K = n, int(info.m_in_view), int(info.k_instances)
     P = width * height
     tiles = info.tiles_x * info.tiles_y
+    cells = (info.tiles_x + 1) * (info.tiles_y + 1)
+    if split:
+        sort = (info.sort_passes - 1) * 16 * K + 12 * K      # (8 read + 8 written) per pass, last pass 8 + 4
+        emit = 24 * M + 8 * K
+    else:
+        sort = info.sort_passes * 24 * K                     # (8+4 read, 8+4 written) per pass
+        emit = 24 * M + 12 * K
     b = {
-        "project": 56 * N + 64 * M,
-        "depth_sort": (4 * N + info.depth_passes * 16 * N) if split else 0,
+        "project": 56 * N + 4 * N + 4 * N + 56 * M,         # planes in; depth key + count for all, record + rect in view
+        "depth_sort": info.depth_passes * 16 * N - 4 * N if split else 0,  # first pass reads keys only
         "scan": (12 if split else 8) * N,
-        "emit": 24 * M + 12 * K,
-        "sort": 8 * K + info.sort_passes * 24 * K,
-        "ranges": 8 * K + 8 * tiles,
-        "composite": 52 * K + 12 * P,
+        "emit": emit,
+        "sort": sort,
+        "ranges": 4 * cells + 8 * tiles,                     # tile_stats: difference grid in, ranges out
+        "composite": 52 * K + 12 * P,                        # upper bound: lists are cut short by early termination
     }
     return b
 
@@ -329,11 +338,18 @@ def run_ours(args):
         stages.append({"stage": k, "ms": round(stage_ms[k], 4), "alg_mb": round(sb[k] / 1e6, 2),
                        "achieved_gbs": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
     dom = max(stages, key=lambda s: s["ms"])
-    kernel_of = {"project": "project_kernel", "depth_sort": "onesweep_kernel<u32> (+histogram)", "scan": "scan_kernel",
-                 "emit": "emit_kernel", "sort": "onesweep_kernel<u64> (+histogram)", "ranges": "ranges_kernel",
-                 "composite": "composite_kernel"}
+    kernel_of = {"project": "project_kernel", "depth_sort": "onesweep_kernel<u32> x4", "scan": "scan_kernel",
+                 "emit": "emit_kernel (+ host read-back of K)", "sort": "onesweep_kernel<u64>", "ranges": "tile_stats_kernel",
+                 "composite": "composite_fast_kernel"}
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this config
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
+        if args.full_cover == 1 and split:
+            traffic = tj.get(args.config, {}).get(dom["stage"])
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": kernel_of[dom["stage"]], "achieved": dom["achieved_gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": dom["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": dom["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
                 "launch_ms": dom["ms"], "stages": stages}
     if dom["stage"] == "composite":
         roofline["note"] = ("compositing is issue-slot bound (fp32 + MUFU.EX2), not HBM bound; the HBM fraction is "
@@ -370,12 +386,16 @@ def run_ours(args):
                                     "steps_executed": int(fr.steps)}
             comp_ms = stage_ms_first.get("composite", 0.0)  # views[0] is orbit view 0 on rank 0
             if comp_ms > 0 and clocks and clocks.get("sm_mhz"):
-                # issue-slot roofline of compositing: ~20 thread-instructions per executed (pixel, Gaussian) step
-                warp_inst = 20.0 * fr.steps / 32.0
+                # issue-slot roofline of compositing.  0.614 warp-instructions per executed (pixel, Gaussian) step
+                # is the ncu count for this kernel on this view (smsp__inst_executed.sum / oracle step count,
+                # profiles/r1_summary.md); the peak is 4 schedulers x 148 SMs x the SM clock sampled during the run.
+                warp_inst = 0.614 * fr.steps
                 peak = 148 * 4 * clocks["sm_mhz"] * 1e6
-                roofline["issue"] = {"steps_view0": int(fr.steps), "est_warp_inst_per_s": warp_inst / (comp_ms * 1e-3),
+                roofline["issue"] = {"kernel": "composite_fast_kernel", "steps_view0": int(fr.steps),
+                                     "composite_ms_view0": comp_ms,
+                                     "warp_inst_per_s": warp_inst / (comp_ms * 1e-3),
                                      "peak_warp_inst_per_s": peak, "frac": warp_inst / (comp_ms * 1e-3) / peak,
-                                     "note": "estimate: 20 instr/step, perfect lane utilisation; see profiles/ for the ncu count"}
+                                     "note": "warp instructions = 0.614 x executed pixel-steps (ncu-calibrated)"}
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)

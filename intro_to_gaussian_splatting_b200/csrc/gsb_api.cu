@@ -329,7 +329,7 @@ int gsb_create(GsbContext** out, int device) {
   GsbContext* c = new (std::nothrow) GsbContext();
   if (!c) return GSB_E_ALLOC;
   c->device = device;
-  if (const char* e = std::getenv("GSB_SORT_ITEMS")) set_sort_items(std::atoi(e));  // tuning knob: 8 (default) or 16
+  if (const char* e = std::getenv("GSB_SORT_ITEMS")) set_sort_items(std::atoi(e));  // tuning knob: 16 (default) or 8
   if (cudaMallocHost((void**)&c->pinned, 64) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }

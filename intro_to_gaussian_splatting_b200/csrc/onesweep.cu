@@ -104,32 +104,35 @@ __device__ __forceinline__ uint32_t digit_fast(KeyT k, int shift, uint32_t mask)
   else return digit32((uint32_t)k, shift, mask);
 }
 
-template <typename KeyT, int kItems, int kMode>
-__global__ void __launch_bounds__(kThreads, kItems == 8 ? 3 : 2)
-onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
-                const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
-                uint32_t* status /* [num_tiles][256] */) {
-  constexpr int kTileKeys = kThreads * kItems;
-  __shared__ union {
-    KeyT keys[kTileKeys];
-    uint32_t vals[kTileKeys];
+template <typename KeyT, int kItems>
+struct SortSmem {
+  union {
+    KeyT keys[kThreads * kItems];
+    uint32_t vals[kThreads * kItems];
   } exch;
-  __shared__ uint32_t s_cnt[kWarps][kRadix];
-  __shared__ uint32_t s_tile_start[kRadix];
-  __shared__ uint32_t s_gofs[kRadix];
-  __shared__ uint32_t s_scan[2][kWarps];
-  __shared__ uint32_t s_tile;
+  uint32_t cnt[kWarps][kRadix];
+  uint32_t tile_start[kRadix];
+  uint32_t gofs[kRadix];
+  uint32_t scan[2][kWarps];
+  uint32_t tile;
+};
 
+// kFull: the tile holds kThreads*kItems keys (every tile but the last) -> straight-line code, no bounds checks
+template <typename KeyT, int kItems, int kMode, bool kFull>
+__device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const KeyT* __restrict__ keys_in,
+                                              const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                                              uint32_t* __restrict__ vals_out, int64_t n, int shift, uint32_t mask,
+                                              const uint32_t* __restrict__ hist, uint32_t* status, uint32_t tile,
+                                              int valid) {
+  constexpr int kTileKeys = kThreads * kItems;
+  auto& exch = sm.exch;
+  auto& s_cnt = sm.cnt;
+  auto& s_tile_start = sm.tile_start;
+  auto& s_gofs = sm.gofs;
+  auto& s_scan = sm.scan;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kWarps * kRadix; i += kThreads) (&s_cnt[0][0])[i] = 0;
-  __syncthreads();
-  const uint32_t tile = s_tile;
   const int64_t base = (int64_t)tile * kTileKeys;
-  const int valid = (int)min((int64_t)kTileKeys, n - base);
-  const bool full = valid == kTileKeys;  // all tiles but the last: no bounds checks
-  const uint32_t mask = (1u << bits) - 1u;
+  constexpr bool full = kFull;
   const KeyT kPad = ~(KeyT)0;
 
   // 2. warp-striped coalesced loads
@@ -149,24 +152,20 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   // 3. stable ranks inside the warp, written for instruction-level parallelism: all matches first, then all
   //    shared-memory atomics (leaders only; an ATOMS returns the running count, and shared atomics of one
   //    warp retire in issue order, which is what keeps equal digits in item order), then all broadcasts.
-  uint32_t info[kItems];  // leader | rank among peers << 8 | peers << 16
+  unsigned peers[kItems];
   uint32_t pos[kItems];
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    const uint32_t d = digit_fast(key[i], shift, mask);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    info[i] = (uint32_t)(__ffs(peers) - 1) | ((uint32_t)__popc(peers & lt_mask) << 8) | ((uint32_t)__popc(peers) << 16);
-  }
+  for (int i = 0; i < kItems; ++i) peers[i] = __match_any_sync(0xffffffffu, digit_fast(key[i], shift, mask));
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     pos[i] = 0;
-    if (((info[i] >> 8) & 255u) == 0u)  // rank 0 among its peers == the leader
-      pos[i] = atomicAdd(&s_cnt[warp][digit_fast(key[i], shift, mask)], info[i] >> 16);
+    if ((peers[i] & lt_mask) == 0u)  // lowest lane of its peer group == the leader
+      pos[i] = atomicAdd(&s_cnt[warp][digit_fast(key[i], shift, mask)], (uint32_t)__popc(peers[i]));
   }
 #pragma unroll
   for (int i = 0; i < kItems; ++i)
-    pos[i] = __shfl_sync(0xffffffffu, pos[i], (int)(info[i] & 31u)) + ((info[i] >> 8) & 255u);
+    pos[i] = __shfl_sync(0xffffffffu, pos[i], __ffs(peers[i]) - 1) + (uint32_t)__popc(peers[i] & lt_mask);
   __syncthreads();
 
   // 4a. thread d owns digit d: scan the warp counters, publish the tile's aggregate as early as possible
@@ -293,10 +292,31 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   }
 }
 
+template <typename KeyT, int kItems, int kMode>
+__global__ void __launch_bounds__(kThreads, kItems == 8 ? 3 : 2)
+onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+                const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
+                uint32_t* status /* [num_tiles][256] */) {
+  constexpr int kTileKeys = kThreads * kItems;
+  __shared__ SortSmem<KeyT, kItems> sm;
+  const int tid = threadIdx.x;
+  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < kWarps * kRadix; i += kThreads) (&sm.cnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+  const int valid = (int)min((int64_t)kTileKeys, n - (int64_t)tile * kTileKeys);
+  const uint32_t mask = (1u << bits) - 1u;
+  if (valid == kTileKeys)
+    onesweep_tile<KeyT, kItems, kMode, true>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
+  else
+    onesweep_tile<KeyT, kItems, kMode, false>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
+}
+
 }  // namespace
 
-static int g_sort_items = 8;  // keys per thread of the onesweep tile (8 or 16); tuning knob, see gsb_api.cu
-void set_sort_items(int items) { g_sort_items = (items == 16) ? 16 : 8; }
+static int g_sort_items = 16;  // keys per thread of the onesweep tile (8 or 16); tuning knob, see gsb_api.cu
+void set_sort_items(int items) { g_sort_items = (items == 8) ? 8 : 16; }
 
 template <typename KeyT>
 SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
