@@ -144,6 +144,12 @@ def make_oracle_inputs(spec_name, full_cover, n_views):
         ocams.append(o)
     arrays = (sc.xyz, sc.scales, sc.quats, (sc.rgb255 / 256).float(), sc.opacity_logit)
     arrays = tuple(a.numpy() for a in arrays)
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    orc.set_num_threads(cores)
     return sc, orc, ocams, orc.default_params(full_cover=full_cover), arrays
 
 

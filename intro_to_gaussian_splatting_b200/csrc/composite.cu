@@ -19,6 +19,8 @@
 //
 // Roofline: issue slots (fp32 FMA/ALU + MUFU.EX2), not HBM: ~20 warp-instructions per
 // (warp, Gaussian) step; HBM traffic is 4 B payload + 48 B record per instance + 12 B per pixel.
+#include <cstdlib>
+
 #include "gsb_internal.cuh"
 
 namespace gsb {
@@ -261,6 +263,137 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// REF_CPU path, packed-fp32 variant (Blackwell): the same 64-thread / 1x4-pixel-column mapping as
+// composite_fast_kernel, but the four pixels are processed as TWO PAIRS with the sm_100 dual-fp32
+// instructions (FFMA2 / FMUL2 / FADD2, PTX fma.rn.f32x2 ...).  Each packed op performs two IEEE-rn
+// operations, bit-identical to two scalar ones, for one issue slot -- and issue slots are what bound this
+// kernel (ncu: issue active 85 %, FMA pipe 65 %, DRAM 1 %).  Per pixel-step: ~12.5 SASS instructions
+// instead of 17.4.
+//
+// Packed operands must sit in aligned register pairs, so every per-Gaussian scalar that multiplies a pixel
+// pair is stored DUPLICATED in shared memory: a record is 5 x float4
+//     {mx,mx,my,my} {a,a,b,b} {c,c,d,d} {op,op,r,r} {g,g,bl,bl}            (a b; c d) = -0.5 * inv cov
+// read with five broadcast LDS.128 per thread-step.  cp.async cannot duplicate, so staging goes through
+// registers (one record per thread per batch of 64, prefetched one batch ahead, double-buffered in smem).
+//
+// Termination: live &= (T >= min_weight) per pixel as before; the colour FMAs are packed, so instead of
+// predicating them the blend weight is zeroed with FSEL when the pixel is no longer live.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPkThreads = 64;
+constexpr int kPkBatch = 64;
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+__global__ void __launch_bounds__(kPkThreads)
+composite_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
+                        const float4* __restrict__ rec, float* __restrict__ image,
+                        const __grid_constant__ CompositeArgs a) {
+  __shared__ __align__(16) float4 sm[2][kPkBatch * 5];
+
+  const int tile = blockIdx.x;
+  const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int px = tx * kTile + (lane & 15);
+  const int py0 = ty * kTile + warp * 8 + (lane >> 4) * 4;
+  const float2 nfx = f2(-(float)px, -(float)px);
+  const float2 nfyA = f2(-(float)py0, -(float)(py0 + 1));
+  const float2 nfyB = f2(-(float)(py0 + 2), -(float)(py0 + 3));
+  const float2 kLog2e = f2(1.4426950408889634f, 1.4426950408889634f);
+  const float2 kNeg1 = f2(-1.f, -1.f);
+  const float minw = a.min_weight;
+
+  const uint2 rg = ranges[tile];
+  const uint32_t len = rg.y - rg.x;
+  const uint32_t* pl = payload + rg.x;
+
+  bool l0 = px < a.width && py0 < a.height, l1 = px < a.width && py0 + 1 < a.height;
+  bool l2 = px < a.width && py0 + 2 < a.height, l3 = px < a.width && py0 + 3 < a.height;
+  float2 TA = f2(1.f, 1.f), TB = f2(1.f, 1.f);
+  float2 RA = f2(0.f, 0.f), GA = RA, BA = RA, RB = RA, GB = RA, BB = RA;
+
+  // register-staged prefetch: this thread's record of the next batch
+  float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, p2 = p0;
+  auto fetch = [&](uint32_t b) {
+    const uint32_t slot = b * kPkBatch + tid;
+    p0 = make_float4(0, 0, 0, 0); p1 = p0; p2 = p0;  // null record: opacity 0 => alpha 0 => exact no-op
+    if (slot < len) {
+      const float4* src = rec + 3 * (size_t)pl[slot];
+      p0 = src[0]; p1 = src[1]; p2 = src[2];
+    }
+  };
+  auto stash = [&](int buf) {
+    float4* d = &sm[buf][tid * 5];
+    d[0] = make_float4(p0.x, p0.x, p0.y, p0.y);  // mx mx my my
+    d[1] = make_float4(p0.z, p0.z, p0.w, p0.w);  // a a b b
+    d[2] = make_float4(p1.x, p1.x, p1.y, p1.y);  // c c d d
+    d[3] = make_float4(p1.z, p1.z, p1.w, p1.w);  // op op r r
+    d[4] = make_float4(p2.x, p2.x, p2.y, p2.y);  // g g bl bl
+  };
+
+  const uint32_t nb = (len + kPkBatch - 1) / kPkBatch;
+  if (nb > 0) { fetch(0); stash(0); }
+  if (nb > 1) fetch(1);
+  bool warp_live = true;
+  for (uint32_t b = 0; b < nb; ++b) {
+    const int buf = (int)(b & 1);
+    __syncthreads();  // batch b visible; everyone is done reading the other buffer
+    if (b + 1 < nb) {
+      stash(buf ^ 1);
+      if (b + 2 < nb) fetch(b + 2);
+    }
+    if (warp_live) {
+      const float4* p = sm[buf];
+#pragma unroll 1
+      for (int i = 0; i < kPkBatch; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
+          p += 5;
+          const float2 dx = __fadd2_rn(f2(q0.x, q0.y), nfx);            // (dx, dx)
+          const float2 ta_ = __fmul2_rn(dx, f2(q1.x, q1.y));            // (dx*a, dx*a)
+          const float2 tb_ = __fmul2_rn(dx, f2(q1.z, q1.w));            // (dx*b, dx*b)
+          const float2 my = f2(q0.z, q0.w), cc = f2(q2.x, q2.y), dd = f2(q2.z, q2.w);
+          const float2 op = f2(q3.x, q3.y), cr = f2(q3.z, q3.w), cg = f2(q4.x, q4.y), cb = f2(q4.z, q4.w);
+#define GSB_PAIR_STEP(NFY, T, LA, LB, R, G, B)                                                   \
+          {                                                                                      \
+            const float2 dy = __fadd2_rn(my, NFY);                                               \
+            const float2 u0 = __ffma2_rn(dy, cc, ta_);                                           \
+            const float2 u1 = __ffma2_rn(dy, dd, tb_);                                           \
+            /* ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS, even with */ \
+            /* --fmad=false); the reference sum is UNFUSED, so the add is done with scalar FADDs */ \
+            const float2 m0 = __fmul2_rn(u0, dx), m1 = __fmul2_rn(u1, dy);                       \
+            const float2 pw = f2(__fadd_rn(m0.x, m1.x), __fadd_rn(m0.y, m1.y));                  \
+            const float2 e = __fmul2_rn(pw, kLog2e);                                             \
+            const float2 al = __fmul2_rn(f2(ex2_approx(e.x), ex2_approx(e.y)), op);              \
+            float2 ta = __fmul2_rn(T, al);                                                       \
+            T = __ffma2_rn(ta, kNeg1, T);                                                        \
+            LA = LA && (T.x >= minw);                                                            \
+            LB = LB && (T.y >= minw);                                                            \
+            ta.x = LA ? ta.x : 0.f;                                                              \
+            ta.y = LB ? ta.y : 0.f;                                                              \
+            R = __ffma2_rn(ta, cr, R); G = __ffma2_rn(ta, cg, G); B = __ffma2_rn(ta, cb, B);     \
+          }
+          GSB_PAIR_STEP(nfyA, TA, l0, l1, RA, GA, BA)
+          GSB_PAIR_STEP(nfyB, TB, l2, l3, RB, GB, BB)
+#undef GSB_PAIR_STEP
+        }
+        if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) { warp_live = false; break; }
+      }
+    }
+    if (!__syncthreads_or(warp_live)) break;
+  }
+  if (px < a.width) {
+    float* o = image + ((size_t)py0 * a.width + px) * 3;
+    const size_t row = (size_t)a.width * 3;
+    if (py0 < a.height) { o[0] = RA.x; o[1] = GA.x; o[2] = BA.x; }
+    if (py0 + 1 < a.height) { o[row] = RA.y; o[row + 1] = GA.y; o[row + 2] = BA.y; }
+    if (py0 + 2 < a.height) { o[2 * row] = RB.x; o[2 * row + 1] = GB.x; o[2 * row + 2] = BB.x; }
+    if (py0 + 3 < a.height) { o[3 * row] = RB.y; o[3 * row + 1] = GB.y; o[3 * row + 2] = BB.y; }
+  }
+}
+
 }  // namespace
 
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
@@ -268,7 +401,14 @@ int launch_composite(const uint2* ranges, const uint32_t* payload, const float4*
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
   CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max};
-  composite_fast_kernel<<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, a);
+  // GSB_COMPOSITE=2 selects the packed-fp32x2 variant (A/B knob).  Measured on B200, config 3: 432 us vs 424 us
+  // for the scalar kernel -- FFMA2/FMUL2/FADD2 halve the issue slots (289 M vs 387 M warp instructions) but
+  // occupy the FMA pipe for two cycles each, so the pipe-bound time is unchanged (profiles/r1_summary.md).
+  static const int variant = [] { const char* e = std::getenv("GSB_COMPOSITE"); return e ? std::atoi(e) : 1; }();
+  if (variant == 2)
+    composite_packed_kernel<<<tiles, kPkThreads, 0, st>>>(ranges, payload, rec, image, a);
+  else
+    composite_fast_kernel<<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, a);
   return (int)cudaGetLastError();
 }
 
