@@ -54,6 +54,8 @@ extern "C" {
 #define GSB_SORT_AUTO 0
 #define GSB_SORT_FULL 1  /* expand in index order, 64-bit LSD onesweep over all K keys */
 #define GSB_SORT_SPLIT 2 /* depth digits sorted per Gaussian (M items) before expansion, tile digits after */
+#define GSB_SORT_BINNED 3 /* per-Gaussian depth sort, instances dropped into exact per-tile segments, each segment
+                            sorted by depth rank in shared memory */
 
 /* Per-view camera constants, exactly the tensors GaussianImage holds (splat/image.py:19-70).
  * Matrices are row-major with the reference's row-vector convention: row = [x y z 1] @ M.

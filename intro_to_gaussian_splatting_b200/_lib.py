@@ -18,6 +18,7 @@ GSB_SEM_REF_CU = 1
 GSB_SORT_AUTO = 0
 GSB_SORT_FULL = 1
 GSB_SORT_SPLIT = 2
+GSB_SORT_BINNED = 3
 GSB_NUM_STAGES = 7
 STAGE_NAMES = ("project", "depth_sort", "scan", "emit", "sort", "ranges", "composite")
 

@@ -282,6 +282,164 @@ int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k,
 }
 
 // ------------------------------------------------------------------------------------------------
+// BINNED mode: per-tile lists without a global sort over the K instances.
+//
+// The exact number of instances of every tile is known before a single key exists (tile_stats_kernel), so
+// every tile owns a fixed segment [start,end) of the payload array.  emit_binned_kernel drops each
+// (Gaussian, tile) instance into its tile's segment through a per-tile atomic cursor -- unordered -- and
+// tile_sort_kernel then sorts each segment BY DEPTH RANK in shared memory.  The depth rank (position of the
+// Gaussian in the stable depth sort of kernel 2) is unique per Gaussian and already encodes the tie order,
+// so sorting a segment by rank reproduces exactly the order the 64-bit key sort would give, with a 20-bit key
+// (N = 1 M) instead of 45 bits, on data that never leaves the SM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+invert_perm_kernel(const uint32_t* __restrict__ order, int64_t n, uint32_t* __restrict__ rank) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) rank[order[j]] = (uint32_t)j;
+}
+
+int launch_invert_perm(const uint32_t* order, int64_t n, uint32_t* rank, cudaStream_t st) {
+  if (n == 0) return 0;
+  invert_perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, n, rank);
+  return (int)cudaGetLastError();
+}
+
+// One warp looks after 32 consecutive Gaussians; those with a non-empty rect are expanded one after the
+// other by the WHOLE warp (32 tiles per step), so a Gaussian covering 2 000 tiles is spread over all lanes.
+__global__ void __launch_bounds__(256)
+emit_binned_kernel(int64_t n, const ushort4* __restrict__ rect, const uint32_t* __restrict__ count, int tiles_x,
+                   const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, uint32_t* __restrict__ payload) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  ushort4 r = make_ushort4(0, 0, 0, 0);
+  uint32_t cnt = 0;
+  if (i < n) { cnt = count[i]; if (cnt) r = rect[i]; }
+  unsigned todo = __ballot_sync(0xffffffffu, cnt != 0);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
+    const uint32_t x0 = __shfl_sync(0xffffffffu, (uint32_t)r.x, src), x1 = __shfl_sync(0xffffffffu, (uint32_t)r.y, src);
+    const uint32_t y0 = __shfl_sync(0xffffffffu, (uint32_t)r.z, src);
+    const uint32_t w = x1 - x0 + 1u;
+    const uint32_t g = (uint32_t)(i - lane + src);
+    for (uint32_t t = lane; t < c; t += 32) {
+      const uint32_t tile = (y0 + t / w) * (uint32_t)tiles_x + x0 + t % w;
+      const uint32_t slot = ranges[tile].x + atomicAdd(&cursor[tile], 1u);
+      payload[slot] = g;
+    }
+  }
+}
+
+int launch_emit_binned(int64_t n, const ushort4* rect, const uint32_t* count, int tiles_x, const uint2* ranges,
+                       uint32_t* cursor, uint32_t* payload, cudaStream_t st) {
+  if (n == 0) return 0;
+  emit_binned_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, rect, count, tiles_x, ranges, cursor, payload);
+  return (int)cudaGetLastError();
+}
+
+// Per-tile LSD radix sort of the segment by depth rank: 8-bit digits, ceil(rank_bits/8) passes, data in
+// shared memory (or, for segments longer than the shared-memory capacity, in the caller's global scratch --
+// the code is the same, only the pointers differ).  Each pass is stable: warp w owns a contiguous slice of
+// the segment and walks it 32 items at a time in order; in-warp ranks come from __match_any_sync, the warp's
+// running per-digit count lives in a counter row, and the rows are combined by an exclusive scan over
+// (digit, warp).  Input payload[start..end) holds Gaussian indices; output the same indices, depth-sorted.
+constexpr int kTsThreads = 256;
+constexpr int kTsWarps = kTsThreads / 32;
+constexpr int kTsBits = 8;
+constexpr int kTsBins = 1 << kTsBits;
+
+__global__ void __launch_bounds__(kTsThreads)
+tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ order,
+                 uint32_t* __restrict__ payload, int rank_bits, uint32_t smem_items, uint32_t* __restrict__ scratch_a,
+                 uint32_t* __restrict__ scratch_b) {
+  extern __shared__ uint32_t s_dyn[];                 // [2][smem_items] ping-pong buffers
+  __shared__ uint32_t s_cnt[kTsWarps][kTsBins];  // per-warp digit counts -> exclusive offsets
+  __shared__ uint32_t s_part[kTsThreads];
+
+  const uint2 rg = ranges[blockIdx.x];
+  const uint32_t L = rg.y - rg.x;
+  if (L == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* A = s_dyn;
+  uint32_t* B = s_dyn + smem_items;
+  if (L > smem_items) { A = scratch_a + rg.x; B = scratch_b + rg.x; }  // long segment: global scratch
+
+  for (uint32_t i = tid; i < L; i += kTsThreads) A[i] = rank[payload[rg.x + i]];
+  if (L > 1) {
+    // contiguous slice per warp, a multiple of 32 items
+    const uint32_t per_warp = ((L + kTsWarps * 32 - 1) / (kTsWarps * 32)) * 32;
+    const uint32_t w0 = min(L, (uint32_t)warp * per_warp), w1 = min(L, w0 + per_warp);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int shift = 0; shift < rank_bits; shift += kTsBits) {
+      for (int t = tid; t < kTsWarps * kTsBins; t += kTsThreads) (&s_cnt[0][0])[t] = 0;
+      __syncthreads();
+      // 1. per-warp digit histogram (one shared atomic per distinct digit of a 32-item step)
+      for (uint32_t b = w0; b < w1; b += 32) {
+        const uint32_t i = b + lane;
+        const uint32_t d = i < w1 ? (A[i] >> shift) & (kTsBins - 1) : 0xFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (i < w1 && (peers & lt_mask) == 0u) s_cnt[warp][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      // 2. exclusive scan over (digit, warp): thread d owns digit d
+      uint32_t local = 0;
+#pragma unroll
+      for (int w = 0; w < kTsWarps; ++w) local += s_cnt[w][tid];
+      uint32_t inc = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      s_part[tid] = inc;
+      __syncthreads();
+      uint32_t run = inc - local;
+      for (int w = 0; w < warp; ++w) run += s_part[w * 32 + 31];
+#pragma unroll
+      for (int w = 0; w < kTsWarps; ++w) {
+        const uint32_t v = s_cnt[w][tid];
+        s_cnt[w][tid] = run;
+        run += v;
+      }
+      __syncthreads();
+      // 3. stable scatter: same walk, the counter row now holds the running output position
+      for (uint32_t b = w0; b < w1; b += 32) {
+        const uint32_t i = b + lane;
+        const uint32_t v = i < w1 ? A[i] : 0u;
+        const uint32_t d = i < w1 ? (v >> shift) & (kTsBins - 1) : 0xFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        uint32_t base = 0;
+        const int leader = __ffs(peers) - 1;
+        if (i < w1 && lane == leader) {
+          base = s_cnt[warp][d];
+          s_cnt[warp][d] = base + (uint32_t)__popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (i < w1) B[base + __popc(peers & lt_mask)] = v;
+        __syncwarp();
+      }
+      __syncthreads();
+      uint32_t* tswap = A; A = B; B = tswap;
+    }
+  } else {
+    __syncthreads();
+  }
+  for (uint32_t i = tid; i < L; i += kTsThreads) payload[rg.x + i] = order[A[i]];
+}
+
+int launch_tile_sort(const uint2* ranges, int tiles, const uint32_t* rank, const uint32_t* order, uint32_t* payload,
+                     int rank_bits, uint32_t* scratch_a, uint32_t* scratch_b, cudaStream_t st) {
+  if (tiles <= 0) return 0;
+  const uint32_t smem_items = 4096;  // 2 x 16 KB of dynamic shared memory: lists up to 4 096 entries stay on the SM
+  const size_t dyn = (size_t)smem_items * 2 * sizeof(uint32_t);
+  tile_sort_kernel<<<(unsigned)tiles, kTsThreads, dyn, st>>>(ranges, rank, order, payload, rank_bits, smem_items,
+                                                            scratch_a, scratch_b);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // tile statistics from the 2-D difference grid written by the projection kernel.
 // One CTA (the grid has (tiles_x+1)*(tiles_y+1) cells: 8 349 at 1080p, 33 k at 4K; it lives in L2).
 //   1. prefix sum along x (one warp per row), 2. prefix sum along y (one thread per column)

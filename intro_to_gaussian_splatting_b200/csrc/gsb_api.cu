@@ -64,13 +64,14 @@ constexpr int kCtlHeaderWords = 16;
 constexpr int kCtlHistWords = kMaxPasses * kRadix;
 
 struct CtlLayout {
-  size_t hist, grid, scan, dsort, total;  // word offsets
+  size_t hist, grid, cursor, scan, dsort, total;  // word offsets
 };
 CtlLayout ctl_layout(FrameGeom g, int64_t n_rows, size_t dsort_words) {
   CtlLayout L;
   L.hist = kCtlHeaderWords;
   L.grid = L.hist + kCtlHistWords;
-  L.scan = L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1);
+  L.cursor = L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1);  // BINNED: one fill cursor per tile
+  L.scan = L.cursor + (size_t)g.tiles_x * (size_t)g.tiles_y;
   L.dsort = L.scan + scan_status_words(n_rows);
   L.total = L.dsort + dsort_words;
   return L;
@@ -85,7 +86,7 @@ struct GsbContext {
   // per-Gaussian frame data
   DevBuf depth_key, rec, rect, count, offsets, bbox;
   DevBuf dbg_cov2d, dbg_conic, dbg_bbox;
-  DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b;
+  DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, rank;
   // per-instance
   DevBuf keys_a, keys_b, vals_a, vals_b;
   DevBuf ranges, control, control2;
@@ -132,7 +133,7 @@ int check_params(const GsbCamera* cam, const GsbParams* prm) {
   if (cam->width <= 0 || cam->height <= 0) return GSB_E_INVALID_ARG;
   if (cam->width > 65535 * kTile || cam->height > 65535 * kTile) return GSB_E_UNSUPPORTED;
   if (prm->semantics != GSB_SEM_REF_CPU && prm->semantics != GSB_SEM_REF_CU) return GSB_E_INVALID_ARG;
-  if (prm->sort_mode < GSB_SORT_AUTO || prm->sort_mode > GSB_SORT_SPLIT) return GSB_E_INVALID_ARG;
+  if (prm->sort_mode < GSB_SORT_AUTO || prm->sort_mode > GSB_SORT_BINNED) return GSB_E_INVALID_ARG;
   return GSB_OK;
 }
 
@@ -211,6 +212,43 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   return GSB_OK;
 }
 
+// BINNED mode: tile stats -> K -> unordered per-tile segments (atomic cursors) -> per-tile sort by depth rank.
+int bin_by_tile(GsbContext* c, int64_t n_rows, const uint32_t* order, FrameGeom geom, uint32_t* ctl, const CtlLayout& L,
+                cudaStream_t st, StageTimer& tm, int* launches) {
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
+  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom, ctl + L.hist + 4 * kRadix,
+                                              c->ranges.as<uint2>(), ctl + 2, st));
+  if (tiles > 0) ++*launches;
+  tm.mark(GSB_STAGE_RANGES);
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 12, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaStreamSynchronize(st));  // the one host round trip of the frame: M and K
+  const int64_t m = c->pinned[0], k = tiles > 0 ? (int64_t)c->pinned[2] : 0;
+  if (k >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;
+  c->info.m_in_view = m;
+  c->info.k_instances = k;
+  GSB_TRY(c->vals_a.ensure((size_t)k * 4 + 4));
+  GSB_TRY(c->keys_a.ensure((size_t)k * 4 + 4));  // scratch for tile segments longer than shared memory
+  GSB_TRY(c->keys_b.ensure((size_t)k * 4 + 4));
+  if (k > 0 && n_rows > 0) {
+    GSB_CUDA_TRY((cudaError_t)launch_emit_binned(n_rows, c->rect.as<ushort4>(), c->count.as<uint32_t>(), geom.tiles_x,
+                                                 c->ranges.as<uint2>(), ctl + L.cursor, c->vals_a.as<uint32_t>(), st));
+    ++*launches;
+    tm.mark(GSB_STAGE_EMIT);
+    const int rank_bits = ceil_log2(n_rows);
+    GSB_CUDA_TRY((cudaError_t)launch_tile_sort(c->ranges.as<uint2>(), (int)tiles, c->rank.as<uint32_t>(), order,
+                                               c->vals_a.as<uint32_t>(), rank_bits, c->keys_a.as<uint32_t>(),
+                                               c->keys_b.as<uint32_t>(), st));
+    ++*launches;
+    c->info.sort_passes = (rank_bits + 7) / 8;
+    tm.mark(GSB_STAGE_SORT);
+  }
+  c->sorted_in_a = true;
+  c->emitted_valid = false;
+  c->keys_materialized = false;
+  return GSB_OK;
+}
+
 void finish_times(GsbContext* c, cudaStream_t st, bool on) {
   c->have_times = false;
   if (!on) return;
@@ -233,7 +271,10 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   const int64_t n = c->n;
   FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
                  tile_grid_dim(cam->height, kTile, prm->full_cover)};
-  const bool split = prm->sort_mode != GSB_SORT_FULL;  // AUTO = SPLIT
+  // AUTO = SPLIT, the fastest measured (config 3: tile sort 183 us vs 562 us FULL; BINNED spends 140 us in the
+  // atomic emit and 370 us in the per-tile sort, profiles/r1_summary.md)
+  const int mode = prm->sort_mode == GSB_SORT_AUTO ? GSB_SORT_SPLIT : prm->sort_mode;
+  const bool split = mode != GSB_SORT_FULL;  // SPLIT and BINNED both sort the depth keys per Gaussian first
   int launches = 0;
   c->have_frame = false;
   c->have_order = false;
@@ -265,9 +306,18 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
     GSB_TRY(depth_sort(c, n, ctl + L.hist, ctl + L.dsort, st, &launches, &dp));
     c->info.depth_passes = dp;
     perm = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
+    if (mode == GSB_SORT_BINNED) {
+      GSB_TRY(c->rank.ensure(rows * 4));
+      GSB_CUDA_TRY((cudaError_t)launch_invert_perm(perm, n, c->rank.as<uint32_t>(), st));
+      ++launches;
+    }
     tm.mark(GSB_STAGE_DEPTH_SORT);
   }
-  GSB_TRY(bin_and_sort(c, n, perm, split, geom, ctl, L, st, tm, &launches));
+  if (mode == GSB_SORT_BINNED) {
+    GSB_TRY(bin_by_tile(c, n, perm, geom, ctl, L, st, tm, &launches));
+  } else {
+    GSB_TRY(bin_and_sort(c, n, perm, split, geom, ctl, L, st, tm, &launches));
+  }
 
   if (!prm->full_cover)  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
     GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
@@ -343,7 +393,7 @@ void gsb_destroy(GsbContext* c) {
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->offsets, &c->bbox,
                     &c->dbg_cov2d, &c->dbg_conic, &c->dbg_bbox, &c->ord_keys_a, &c->ord_keys_b, &c->ord_vals_a,
-                    &c->ord_vals_b, &c->keys_a, &c->keys_b, &c->vals_a, &c->vals_b, &c->ranges, &c->control,
+                    &c->ord_vals_b, &c->rank, &c->keys_a, &c->keys_b, &c->vals_a, &c->vals_b, &c->ranges, &c->control,
                     &c->control2, &c->image, &c->image2, &c->scratch};
   for (DevBuf* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);

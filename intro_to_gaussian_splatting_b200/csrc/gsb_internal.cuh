@@ -84,6 +84,16 @@ int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* t
 int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
                         uint64_t* keys, cudaStream_t st);
 
+// ---- BINNED mode (binning.cu) ----
+int launch_invert_perm(const uint32_t* order, int64_t n, uint32_t* rank, cudaStream_t st);
+// cursor: one zeroed u32 per tile; payload[ranges[t].x + k] receives the Gaussian indices of tile t, unordered
+int launch_emit_binned(int64_t n, const ushort4* rect, const uint32_t* count, int tiles_x, const uint2* ranges,
+                       uint32_t* cursor, uint32_t* payload, cudaStream_t st);
+// sorts every tile segment of payload by rank[g]; rank_bits = ceil(log2(N)); scratch_{a,b}: K u32 each (only
+// touched by segments longer than the shared-memory capacity)
+int launch_tile_sort(const uint2* ranges, int tiles, const uint32_t* rank, const uint32_t* order, uint32_t* payload,
+                     int rank_bits, uint32_t* scratch_a, uint32_t* scratch_b, cudaStream_t st);
+
 // ---- onesweep radix sort ----
 struct SortPlan {
   int begin_bit, end_bit, passes;

@@ -54,7 +54,8 @@ class GaussianScene(nn.Module):
             self.images[idx] = GaussianImage(camera=camera_dict[image.camera_id], image=image)
         self.gaussians = gaussians
         self.full_cover = bool(full_cover)  # False = the reference tile grid (last row/column never rendered)
-        self.sort_mode = {"auto": _lib.GSB_SORT_AUTO, "full": _lib.GSB_SORT_FULL, "split": _lib.GSB_SORT_SPLIT}[sort_mode]
+        self.sort_mode = {"auto": _lib.GSB_SORT_AUTO, "full": _lib.GSB_SORT_FULL, "split": _lib.GSB_SORT_SPLIT,
+                          "binned": _lib.GSB_SORT_BINNED}[sort_mode]
         self._rast: Optional[Rasterizer] = None
         self._uploaded_sig = None
 

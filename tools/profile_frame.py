@@ -28,7 +28,7 @@ cams, imgs = read_camera_file(d), read_image_file(d)
 packed = [GaussianImage(cams[imgs[i].camera_id], imgs[i]).pack() for i in sorted(imgs)]
 r = Rasterizer(0)
 r.upload(sc.xyz.cuda(), sc.scales.cuda(), sc.quats.cuda(), (sc.rgb255 / 256).float().cuda(), sc.opacity_logit.cuda())
-mode = {"auto": 0, "full": 1, "split": 2}[a.sort_mode]
+mode = {"auto": 0, "full": 1, "split": 2, "binned": 3}[a.sort_mode]
 prm = _lib.default_params(full_cover=a.full_cover, sort_mode=mode, collect_stage_times=a.stage_times)
 img = torch.empty((sc.spec.height, sc.spec.width, 3), device="cuda")
 for f in range(a.frames):
