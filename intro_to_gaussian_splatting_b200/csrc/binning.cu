@@ -40,20 +40,33 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 }  // namespace
 
-size_t scan_status_words(int64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile) + 2; }
+// u32 words of status memory: a ticket (2 words) + one 64-bit (flag | value) word per logical block.
+// 64-bit words because the running total K may exceed the 30 bits a 32-bit word leaves next to its flags.
+size_t scan_status_words(int64_t n) { return 2 * ((size_t)((n + kScanTile - 1) / kScanTile) + 2); }
 
-// Decoupled look-back exclusive scan (one pass over the data).  status[0] is the ticket counter,
-// status[1 + b] the (flag | value) word of logical block b.
+__device__ __forceinline__ uint64_t ld_relaxed64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Decoupled look-back exclusive scan (one pass over the data).  status[0] is the ticket counter; the
+// 64-bit (flag << 62 | value) word of logical block b lives at ((uint64_t*)status)[1 + b].
+// Offsets are u32 (K < 2^32 is checked by the host from tile_stats' 64-bit total).
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
             uint32_t* __restrict__ offsets, uint32_t* __restrict__ total, uint32_t* status) {
+  constexpr uint64_t kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
   __shared__ uint32_t s_block;
   __shared__ uint32_t s_warp[kScanThreads / 32];
   __shared__ uint32_t s_excl;
   if (threadIdx.x == 0) s_block = atomicAdd(&status[0], 1u);  // ticket: predecessors are already running
   __syncthreads();
   const uint32_t b = s_block;
-  uint32_t* st = status + 1;
+  uint64_t* st = reinterpret_cast<uint64_t*>(status) + 1;
   const int64_t base = (int64_t)b * kScanTile + (int64_t)threadIdx.x * kScanItems;
 
   uint32_t v[kScanItems];
@@ -85,35 +98,38 @@ scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
   }
   const uint32_t thread_excl = warp_off + inc - local;
 
-  // publish the aggregate, then look back for the exclusive prefix of this block
+  // publish the aggregate, then look back (a window of 32 predecessors per round) for the exclusive prefix
   if (warp == 0) {
-    uint32_t excl = 0;
+    uint64_t excl = 0;
     if (b == 0) {
-      if (lane == 0) st_relaxed(&st[0], kFlagPrefix | block_sum);
+      if (lane == 0) st_relaxed64(&st[0], kPre | (uint64_t)block_sum);
     } else {
-      if (lane == 0) st_relaxed(&st[b], kFlagAggregate | block_sum);
+      if (lane == 0) st_relaxed64(&st[b], kAgg | (uint64_t)block_sum);
       int64_t idx = (int64_t)b - 1;
       while (true) {
         int64_t j = idx - lane;
-        uint32_t s = kFlagPrefix;  // virtual block -1: inclusive prefix 0
+        uint64_t s = kPre;  // virtual block -1: inclusive prefix 0
         if (j >= 0) {
-          s = ld_relaxed(&st[j]);
-          while ((s >> kFlagShift) == 0) s = ld_relaxed(&st[j]);
+          s = ld_relaxed64(&st[j]);
+          while ((s >> 62) == 0) s = ld_relaxed64(&st[j]);
         }
-        unsigned pm = __ballot_sync(0xffffffffu, (s >> kFlagShift) == 2u);
+        unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2u);
+        uint64_t contrib = s & kMask;
         if (pm) {
           int first = __ffs(pm) - 1;
-          excl += warp_sum(lane <= first ? (s & kValueMask) : 0u);
-          break;
+          if (lane > first) contrib = 0;
         }
-        excl += warp_sum(s & kValueMask);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (pm) break;
         idx -= 32;
       }
-      if (lane == 0) st_relaxed(&st[b], kFlagPrefix | (excl + block_sum));
+      if (lane == 0) st_relaxed64(&st[b], kPre | ((excl + block_sum) & kMask));
     }
     if (lane == 0) {
-      s_excl = excl;
-      if ((int64_t)(b + 1) * kScanTile >= n) *total = excl + block_sum;
+      s_excl = (uint32_t)excl;
+      if ((int64_t)(b + 1) * kScanTile >= n) *total = (uint32_t)(excl + block_sum);
     }
   }
   __syncthreads();
@@ -506,12 +522,23 @@ tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, 
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  uint32_t off = 0, total = 0;
+  uint32_t off = 0;
   for (int w = 0; w < kStatThreads / 32; ++w) {
     const uint32_t t = s_warp[w];
     if (w < warp) off += t;
-    total += t;
   }
+  // exact 64-bit total (the u32 scan above wraps when K >= 2^32; the host then rejects the frame)
+  __shared__ unsigned long long s_total;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  {
+    unsigned long long l64 = local;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l64 += __shfl_xor_sync(0xffffffffu, l64, o);
+    if (lane == 0) atomicAdd(&s_total, l64);
+  }
+  __syncthreads();
+  const unsigned long long total64 = s_total;
   uint32_t run = off + inc - local;
   // histogram rows: row p counts digit (tile >> 8p) & 255.  A thread's tiles are consecutive, so the
   // higher digits repeat: accumulate runs locally and issue one shared atomic per run.
@@ -539,7 +566,10 @@ tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, 
     if (acc[p - 1]) atomicAdd(&s_hist[p][cur[p - 1]], acc[p - 1]);
   __syncthreads();
   for (int t = tid; t < 4 * kRadix; t += kStatThreads) tile_hist[t] = (&s_hist[0][0])[t];
-  if (tid == 0) *k_total = total;
+  if (tid == 0) {  // 64-bit total: the host rejects K >= 2^32 (positions are u32)
+    k_total[0] = (uint32_t)total64;
+    k_total[1] = (uint32_t)(total64 >> 32);
+  }
 }
 
 int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,

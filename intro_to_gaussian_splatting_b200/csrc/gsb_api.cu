@@ -58,7 +58,7 @@ int ceil_log2(int64_t v) {
 }
 
 // control block, zeroed once per frame:
-//   [hdr 16: 0 = M, 1 = K (scan), 2 = K (tile grid)] [hist 8 x 256: rows 0-3 depth digits, 4-7 tile digits]
+//   [hdr 16: 0 = M, 1 = K mod 2^32 (scan), 2-3 = K (tile grid, 64-bit)] [hist 8 x 256: rows 0-3 depth digits, 4-7 tile digits]
 //   [difference grid (tiles_x+1)*(tiles_y+1)] [scan look-back status] [depth-sort tickets + status]
 constexpr int kCtlHeaderWords = 16;
 constexpr int kCtlHistWords = kMaxPasses * kRadix;
@@ -67,13 +67,14 @@ struct CtlLayout {
   size_t hist, grid, cursor, scan, dsort, total;  // word offsets
 };
 CtlLayout ctl_layout(FrameGeom g, int64_t n_rows, size_t dsort_words) {
+  auto up4 = [](size_t w) { return (w + 3) & ~(size_t)3; };  // sections start 16-byte aligned (64-bit status words)
   CtlLayout L;
   L.hist = kCtlHeaderWords;
   L.grid = L.hist + kCtlHistWords;
-  L.cursor = L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1);  // BINNED: one fill cursor per tile
-  L.scan = L.cursor + (size_t)g.tiles_x * (size_t)g.tiles_y;
-  L.dsort = L.scan + scan_status_words(n_rows);
-  L.total = L.dsort + dsort_words;
+  L.cursor = up4(L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1));  // BINNED: one fill cursor per tile
+  L.scan = up4(L.cursor + (size_t)g.tiles_x * (size_t)g.tiles_y);
+  L.dsort = up4(L.scan + scan_status_words(n_rows));
+  L.total = up4(L.dsort + dsort_words);
   return L;
 }
 
@@ -173,11 +174,13 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   if (tiles > 0) ++*launches;
   tm.mark(GSB_STAGE_RANGES);
   // the one host round trip of the frame: M and K
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 12, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 16, cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
-  const int64_t m = c->pinned[0], k = c->pinned[1];
-  if (tiles > 0 && (int64_t)c->pinned[2] != k) return GSB_E_INTERNAL;  // scan and tile grid must agree
-  if (k >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;               // look-back words carry 30-bit counts
+  const int64_t m = c->pinned[0];
+  const int64_t k64 = tiles > 0 ? (int64_t)(((uint64_t)c->pinned[3] << 32) | c->pinned[2]) : 0;
+  if (k64 >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;         // payload positions and ranges are u32
+  const int64_t k = k64;
+  if (tiles > 0 && (int64_t)c->pinned[1] != k) return GSB_E_INTERNAL;  // scan and tile grid must agree
   c->info.m_in_view = m;
   c->info.k_instances = k;
 
@@ -221,10 +224,11 @@ int bin_by_tile(GsbContext* c, int64_t n_rows, const uint32_t* order, FrameGeom 
                                               c->ranges.as<uint2>(), ctl + 2, st));
   if (tiles > 0) ++*launches;
   tm.mark(GSB_STAGE_RANGES);
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 12, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 16, cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));  // the one host round trip of the frame: M and K
-  const int64_t m = c->pinned[0], k = tiles > 0 ? (int64_t)c->pinned[2] : 0;
-  if (k >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;
+  const int64_t m = c->pinned[0];
+  const int64_t k = tiles > 0 ? (int64_t)(((uint64_t)c->pinned[3] << 32) | c->pinned[2]) : 0;
+  if (k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
   c->info.m_in_view = m;
   c->info.k_instances = k;
   GSB_TRY(c->vals_a.ensure((size_t)k * 4 + 4));
@@ -345,7 +349,7 @@ const char* gsb_error_string(int s) {
     case GSB_E_INVALID_ARG: return "invalid argument";
     case GSB_E_NO_SCENE: return "no Gaussians uploaded (call gsb_upload first)";
     case GSB_E_NO_FRAME: return "no frame rendered yet";
-    case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; K < 2^30)";
+    case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; fewer than 2^32-1 tile instances)";
     case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case GSB_E_ALLOC: return "device memory allocation failed";
     case GSB_E_INTERNAL: return "internal consistency check failed (scan total != tile-grid total)";
@@ -379,7 +383,12 @@ int gsb_create(GsbContext** out, int device) {
   GsbContext* c = new (std::nothrow) GsbContext();
   if (!c) return GSB_E_ALLOC;
   c->device = device;
-  if (const char* e = std::getenv("GSB_SORT_ITEMS")) set_sort_items(std::atoi(e));  // tuning knob: 16 (default) or 8
+  {  // process-wide tuning / test knobs, re-read whenever a context is created
+    const char* e = std::getenv("GSB_SORT_ITEMS");        // onesweep keys per thread: 16 (default) or 8
+    set_sort_items(e ? std::atoi(e) : 16);
+    e = std::getenv("GSB_FORCE_WIDE_STATUS");             // 1: 64-bit look-back words even below 2^30 keys
+    set_force_wide_status(e ? std::atoi(e) : 0);
+  }
   if (cudaMallocHost((void**)&c->pinned, 64) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }
@@ -735,7 +744,7 @@ int gsb_stage_times(GsbContext* c, float ms[GSB_NUM_STAGES]) {
 int gsb_sort_pairs_u64(GsbContext* c, int64_t n, uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out,
                        uint32_t* vals_out, int32_t begin_bit, int32_t end_bit, void* stream) {
   if (!c || n < 0 || begin_bit < 0 || end_bit > 64 || end_bit < begin_bit) return GSB_E_INVALID_ARG;
-  if (n >= ((int64_t)1 << 30)) return GSB_E_UNSUPPORTED;
+  if (n >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;
   if (n > 0 && (!keys_in || !vals_in || !keys_out || !vals_out)) return GSB_E_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   GSB_CUDA_TRY(cudaSetDevice(c->device));

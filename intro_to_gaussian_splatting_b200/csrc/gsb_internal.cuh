@@ -99,11 +99,13 @@ struct SortPlan {
   int begin_bit, end_bit, passes;
   int items;              // keys per thread (8 or 16)
   int keys_only;          // 1: payload packed in unsorted key bits; last pass writes low 32 bits to vals
+  int wide_status;        // 1: 64-bit look-back words (2^30 keys and more)
   int64_t n;
   int64_t tiles;          // onesweep tiles per pass
   size_t control_words;   // u32 words of control memory (tickets + look-back status), zeroed by the caller
 };
 void set_sort_items(int items);
+void set_force_wide_status(int on);
 template <typename KeyT>
 SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit);
 // digit histograms computed from the keys (stand-alone sort only); hist = kMaxPasses*256 zeroed words

@@ -44,6 +44,26 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Look-back status word: 2 flag bits + value.  32-bit words carry 30-bit counts (enough below 2^30 keys);
+// sorts of 2^30 .. 2^32-1 keys use 64-bit words.
+template <typename W> struct StatusWord;
+template <> struct StatusWord<uint32_t> {
+  static constexpr int kShift = 30;
+  static __device__ __forceinline__ uint32_t ld(const uint32_t* p) { return ld_relaxed(p); }
+  static __device__ __forceinline__ void st(uint32_t* p, uint32_t v) { st_relaxed(p, v); }
+};
+template <> struct StatusWord<uint64_t> {
+  static constexpr int kShift = 62;
+  static __device__ __forceinline__ uint64_t ld(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  }
+};
+
 template <typename KeyT>
 __device__ __forceinline__ uint32_t digit_of(KeyT k, int shift, uint32_t mask) {
   return (uint32_t)(k >> shift) & mask;
@@ -118,12 +138,14 @@ struct SortSmem {
 };
 
 // kFull: the tile holds kThreads*kItems keys (every tile but the last) -> straight-line code, no bounds checks
-template <typename KeyT, int kItems, int kMode, bool kFull>
+template <typename KeyT, int kItems, int kMode, bool kFull, typename W>
 __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const KeyT* __restrict__ keys_in,
                                               const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                               uint32_t* __restrict__ vals_out, int64_t n, int shift, uint32_t mask,
-                                              const uint32_t* __restrict__ hist, uint32_t* status, uint32_t tile,
+                                              const uint32_t* __restrict__ hist, W* status, uint32_t tile,
                                               int valid) {
+  using SW = StatusWord<W>;
+  constexpr W kWAgg = (W)1 << SW::kShift, kWPre = (W)2 << SW::kShift, kWMask = ((W)1 << SW::kShift) - 1;
   constexpr int kTileKeys = kThreads * kItems;
   auto& exch = sm.exch;
   auto& s_cnt = sm.cnt;
@@ -170,7 +192,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
 
   // 4a. thread d owns digit d: scan the warp counters, publish the tile's aggregate as early as possible
   uint32_t real, tile_start, bin_base;
-  uint32_t* st = status + (size_t)tile * kRadix + tid;
+  W* st = status + (size_t)tile * kRadix + tid;
   {
     const int d = tid;
     uint32_t sum = 0;
@@ -183,7 +205,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     // padding keys (all ones) sit in the highest used bin and, being last in tile order, last in it
     real = sum;
     if ((uint32_t)d == mask) real -= (uint32_t)(kTileKeys - valid);
-    st_relaxed(st, (tile == 0 ? kFlagPrefix : kFlagAggregate) | real);
+    SW::st(st, (tile == 0 ? kWPre : kWAgg) | (W)real);
 
     // block-wide exclusive scans: local tile counts (-> smem layout) and the global histogram (-> bin bases)
     uint32_t a = sum, b = hist[d];
@@ -221,39 +243,39 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   {
     uint32_t excl = 0;
     if (tile != 0) {
-      const uint32_t* col = status + tid;  // status is [tile][256]
+      const W* col = status + tid;  // status is [tile][256]
       int64_t t = (int64_t)tile - 1;
       bool found = false;
       {
-        uint32_t v[2];
+        W v[2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t)(t - k) * kRadix) : kFlagPrefix;
+        for (int k = 0; k < 2; ++k) v[k] = (t - k >= 0) ? SW::ld(col + (size_t)(t - k) * kRadix) : kWPre;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           if (found) break;
-          uint32_t x = v[k];
-          while ((x >> kFlagShift) == 0) x = ld_relaxed(col + (size_t)(t - k) * kRadix);
-          excl += x & kValueMask;
-          found = (x >> kFlagShift) == 2u;
+          W x = v[k];
+          while ((x >> SW::kShift) == 0) x = SW::ld(col + (size_t)(t - k) * kRadix);
+          excl += (uint32_t)(x & kWMask);
+          found = (x >> SW::kShift) == 2u;
         }
         t -= 2;
       }
       while (!found) {
-        uint32_t v[kLookBatch];
+        W v[kLookBatch];
 #pragma unroll
         for (int k = 0; k < kLookBatch; ++k)
-          v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t)(t - k) * kRadix) : kFlagPrefix;
+          v[k] = (t - k >= 0) ? SW::ld(col + (size_t)(t - k) * kRadix) : kWPre;
 #pragma unroll
         for (int k = 0; k < kLookBatch; ++k) {
           if (found) break;
-          uint32_t x = v[k];
-          while ((x >> kFlagShift) == 0) x = ld_relaxed(col + (size_t)(t - k) * kRadix);
-          excl += x & kValueMask;
-          found = (x >> kFlagShift) == 2u;
+          W x = v[k];
+          while ((x >> SW::kShift) == 0) x = SW::ld(col + (size_t)(t - k) * kRadix);
+          excl += (uint32_t)(x & kWMask);
+          found = (x >> SW::kShift) == 2u;
         }
         t -= kLookBatch;
       }
-      st_relaxed(st, kFlagPrefix | ((excl + real) & kValueMask));
+      SW::st(st, kWPre | (((W)excl + (W)real) & kWMask));
     }
     s_gofs[tid] = bin_base + excl - tile_start;  // global index = s_gofs[d] + local position (mod 2^32)
   }
@@ -292,12 +314,12 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   }
 }
 
-template <typename KeyT, int kItems, int kMode>
+template <typename KeyT, int kItems, int kMode, typename W>
 __global__ void __launch_bounds__(kThreads, kItems == 8 ? 3 : 2)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                 const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
-                uint32_t* status /* [num_tiles][256] */) {
+                W* status /* [num_tiles][256] */) {
   constexpr int kTileKeys = kThreads * kItems;
   __shared__ SortSmem<KeyT, kItems> sm;
   const int tid = threadIdx.x;
@@ -308,15 +330,17 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   const int valid = (int)min((int64_t)kTileKeys, n - (int64_t)tile * kTileKeys);
   const uint32_t mask = (1u << bits) - 1u;
   if (valid == kTileKeys)
-    onesweep_tile<KeyT, kItems, kMode, true>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
+    onesweep_tile<KeyT, kItems, kMode, true, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
   else
-    onesweep_tile<KeyT, kItems, kMode, false>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
+    onesweep_tile<KeyT, kItems, kMode, false, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
 }
 
 }  // namespace
 
 static int g_sort_items = 16;  // keys per thread of the onesweep tile (8 or 16); tuning knob, see gsb_api.cu
 void set_sort_items(int items) { g_sort_items = (items == 8) ? 8 : 16; }
+static int g_force_wide = 0;   // test knob: use the 64-bit look-back words regardless of the key count
+void set_force_wide_status(int on) { g_force_wide = on ? 1 : 0; }
 
 template <typename KeyT>
 SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
@@ -330,8 +354,9 @@ SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
   p.items = g_sort_items;
   const int64_t tile_keys = (int64_t)kThreads * p.items;
   p.tiles = (n + tile_keys - 1) / tile_keys;
-  // [tickets: 8][status: passes * tiles * 256]
-  p.control_words = 8 + (size_t)p.passes * (size_t)p.tiles * kRadix;
+  // [tickets: 8][status: passes * tiles * 256 words; 64-bit words from 2^30 keys on]
+  p.wide_status = (g_force_wide || n >= ((int64_t)1 << 30)) ? 1 : 0;
+  p.control_words = 8 + (size_t)p.passes * (size_t)p.tiles * kRadix * (p.wide_status ? 2 : 1);
   return p;
 }
 template SortPlan make_sort_plan<uint32_t>(int64_t, int, int);
@@ -350,16 +375,16 @@ int launch_key_histogram(const SortPlan& plan, const KeyT* keys, uint32_t* hist,
 template int launch_key_histogram<uint32_t>(const SortPlan&, const uint32_t*, uint32_t*, cudaStream_t);
 template int launch_key_histogram<uint64_t>(const SortPlan&, const uint64_t*, uint32_t*, cudaStream_t);
 
-template <typename KeyT, int kItems>
+template <typename KeyT, int kItems, typename W>
 static void launch_pass(int mode, unsigned tiles, cudaStream_t st, const KeyT* kin, const uint32_t* vin, KeyT* kout,
                         uint32_t* vout, int64_t n, int shift, int bits, const uint32_t* hist, uint32_t* ticket,
-                        uint32_t* status) {
+                        W* status) {
   if (mode == kPairs)
-    onesweep_kernel<KeyT, kItems, kPairs><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+    onesweep_kernel<KeyT, kItems, kPairs, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
   else if (mode == kKeysOnly)
-    onesweep_kernel<KeyT, kItems, kKeysOnly><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+    onesweep_kernel<KeyT, kItems, kKeysOnly, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
   else
-    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
 }
 
 template <typename KeyT>
@@ -379,14 +404,22 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
   for (int p = 0; p < plan.passes; ++p) {
     const int shift = plan.begin_bit + p * kRadixBits;
     const int bits = (plan.end_bit - shift) < kRadixBits ? (plan.end_bit - shift) : kRadixBits;
-    uint32_t* stp = status + (size_t)p * (size_t)plan.tiles * kRadix;
+    const size_t per_pass = (size_t)plan.tiles * kRadix;
     const int mode = !plan.keys_only ? kPairs : (p == plan.passes - 1 ? kKeysOnlyLowOut : kKeysOnly);
-    if (plan.items == 16)
-      launch_pass<KeyT, 16>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits,
-                            hist + (size_t)p * kRadix, tickets + p, stp);
-    else
-      launch_pass<KeyT, 8>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits,
-                           hist + (size_t)p * kRadix, tickets + p, stp);
+    const uint32_t* h = hist + (size_t)p * kRadix;
+    if (plan.wide_status) {
+      uint64_t* stp = reinterpret_cast<uint64_t*>(status) + (size_t)p * per_pass;  // status starts 8-byte aligned
+      if (plan.items == 16)
+        launch_pass<KeyT, 16, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+      else
+        launch_pass<KeyT, 8, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+    } else {
+      uint32_t* stp = status + (size_t)p * per_pass;
+      if (plan.items == 16)
+        launch_pass<KeyT, 16, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+      else
+        launch_pass<KeyT, 8, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+    }
     if (launches) ++*launches;
     kin = kout; vin = vout;
     if (kout == keys_b) { kout = keys_a; vout = vals_a; } else { kout = keys_b; vout = vals_b; }

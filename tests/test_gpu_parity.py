@@ -188,3 +188,42 @@ def test_sort_standalone(rast):
             order = np.argsort(ku & mask, kind="stable")
             assert np.array_equal(u64(ko), ku[order]), (n, b, e)
             assert np.array_equal(vo.cpu().numpy(), vals.numpy()[order]), (n, b, e)
+
+
+def test_wide_status_words_and_small_sort_tiles():
+    """The 64-bit look-back path (used from 2^30 keys on) and the 8-keys-per-thread tile, forced through the
+    environment knobs read at context creation; same bit-exact contract."""
+    import os
+    sc, images, _ = scene_and_images("cfg2")
+    cam = images[1].pack()
+    fr_cache = {}
+    for env in ({"GSB_FORCE_WIDE_STATUS": "1"}, {"GSB_SORT_ITEMS": "8"}, {"GSB_FORCE_WIDE_STATUS": "1", "GSB_SORT_ITEMS": "8"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            r = Rasterizer(0)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        try:
+            _upload(r, sc)
+            for sm in (_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT):
+                prm = _lib.default_params(sort_mode=sm)
+                img = r.render(cam, prm)
+                torch.cuda.synchronize()
+                if "fr" not in fr_cache:
+                    fr_cache["fr"] = orc.render(to_oracle_camera(cam), to_oracle_params(prm), *scene_arrays(sc))
+                _check_frame_against_oracle(r, fr_cache["fr"], prm)
+                assert np.abs(img.cpu().numpy() - fr_cache["fr"].image).max() <= PIXEL_TOL
+            g = torch.Generator().manual_seed(3)
+            keys = torch.randint(-(2 ** 62), 2 ** 62, (300_000,), generator=g, dtype=torch.int64)
+            vals = torch.arange(300_000, dtype=torch.int32)
+            ko, vo = r.sort_pairs(keys.cuda(), vals.cuda(), 0, 64)
+            order = np.argsort(keys.numpy().view(np.uint64), kind="stable")
+            assert np.array_equal(u64(ko), keys.numpy().view(np.uint64)[order]) and np.array_equal(vo.cpu().numpy(), order.astype(np.int32))
+        finally:
+            r.close()
+    Rasterizer(0).close()  # restore the defaults for later contexts in this process
