@@ -34,16 +34,6 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
   return v;
 }
 
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-}  // namespace
-
-// u32 words of status memory: a ticket (2 words) + one 64-bit (flag | value) word per logical block.
-// 64-bit words because the running total K may exceed the 30 bits a 32-bit word leaves next to its flags.
-size_t scan_status_words(int64_t n) { return 2 * ((size_t)((n + kScanTile - 1) / kScanTile) + 2); }
-
 __device__ __forceinline__ uint64_t ld_relaxed64(const uint64_t* p) {
   uint64_t v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -53,101 +43,7 @@ __device__ __forceinline__ void st_relaxed64(uint64_t* p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Decoupled look-back exclusive scan (one pass over the data).  status[0] is the ticket counter; the
-// 64-bit (flag << 62 | value) word of logical block b lives at ((uint64_t*)status)[1 + b].
-// Offsets are u32 (K < 2^32 is checked by the host from tile_stats' 64-bit total).
-__global__ void __launch_bounds__(kScanThreads)
-scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
-            uint32_t* __restrict__ offsets, uint32_t* __restrict__ total, uint32_t* status) {
-  constexpr uint64_t kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
-  __shared__ uint32_t s_block;
-  __shared__ uint32_t s_warp[kScanThreads / 32];
-  __shared__ uint32_t s_excl;
-  if (threadIdx.x == 0) s_block = atomicAdd(&status[0], 1u);  // ticket: predecessors are already running
-  __syncthreads();
-  const uint32_t b = s_block;
-  uint64_t* st = reinterpret_cast<uint64_t*>(status) + 1;
-  const int64_t base = (int64_t)b * kScanTile + (int64_t)threadIdx.x * kScanItems;
-
-  uint32_t v[kScanItems];
-  uint32_t local = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    int64_t i = base + k;
-    uint32_t c = 0;
-    if (i < n) c = perm ? count[perm[i]] : count[i];
-    v[k] = local;  // exclusive within the thread
-    local += c;
-  }
-  // block exclusive scan of the per-thread sums
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  uint32_t warp_off = 0, block_sum = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w) {
-    uint32_t t = s_warp[w];
-    if (w < warp) warp_off += t;
-    block_sum += t;
-  }
-  const uint32_t thread_excl = warp_off + inc - local;
-
-  // publish the aggregate, then look back (a window of 32 predecessors per round) for the exclusive prefix
-  if (warp == 0) {
-    uint64_t excl = 0;
-    if (b == 0) {
-      if (lane == 0) st_relaxed64(&st[0], kPre | (uint64_t)block_sum);
-    } else {
-      if (lane == 0) st_relaxed64(&st[b], kAgg | (uint64_t)block_sum);
-      int64_t idx = (int64_t)b - 1;
-      while (true) {
-        int64_t j = idx - lane;
-        uint64_t s = kPre;  // virtual block -1: inclusive prefix 0
-        if (j >= 0) {
-          s = ld_relaxed64(&st[j]);
-          while ((s >> 62) == 0) s = ld_relaxed64(&st[j]);
-        }
-        unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2u);
-        uint64_t contrib = s & kMask;
-        if (pm) {
-          int first = __ffs(pm) - 1;
-          if (lane > first) contrib = 0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl += contrib;
-        if (pm) break;
-        idx -= 32;
-      }
-      if (lane == 0) st_relaxed64(&st[b], kPre | ((excl + block_sum) & kMask));
-    }
-    if (lane == 0) {
-      s_excl = (uint32_t)excl;
-      if ((int64_t)(b + 1) * kScanTile >= n) *total = (uint32_t)(excl + block_sum);
-    }
-  }
-  __syncthreads();
-  const uint32_t off = s_excl + thread_excl;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    int64_t i = base + k;
-    if (i < n) offsets[i] = off + v[k];
-  }
-}
-
-int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* total,
-                uint32_t* status, cudaStream_t st) {
-  if (n == 0) return (int)cudaMemsetAsync(total, 0, 4, st);
-  unsigned blocks = (unsigned)((n + kScanTile - 1) / kScanTile);
-  scan_kernel<<<blocks, kScanThreads, 0, st>>>(count, perm, n, offsets, total, status);
-  return (int)cudaGetLastError();
-}
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // emit: output-parallel expansion.  A block owns 256 consecutive Gaussians (in emission order) and
@@ -161,31 +57,83 @@ int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
+// u32 words of status memory for emit's fused scan: a ticket (2 words) + one 64-bit word per CTA
+size_t emit_status_words(int64_t n) { return 2 * ((size_t)((n + kEmitThreads - 1) / kEmitThreads) + 2); }
+
 template <bool kCombined>
 __global__ void __launch_bounds__(kEmitThreads)
-emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
-            int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
-            uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+emit_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
+            const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
+            uint64_t* __restrict__ keys, uint32_t* __restrict__ payload, uint32_t* status) {
   __shared__ uint32_t s_off[kEmitThreads + 1];
   __shared__ uint32_t s_gid[kEmitThreads];
   __shared__ uint32_t s_low[kEmitThreads];  // low key word: depth bits (FULL) or Gaussian index (SPLIT)
   __shared__ ushort4 s_rect[kEmitThreads];
-  const int64_t base = (int64_t)blockIdx.x * kEmitThreads;
-  const int64_t i = base + threadIdx.x;
-  uint32_t off = 0;
+  __shared__ uint32_t s_block, s_excl;
+  __shared__ uint32_t s_warp[kEmitThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- fused exclusive scan of the tile counts in emission order (single pass, decoupled look-back) ----
+  // status[0] = ticket (logical CTA order == launch order of the predecessors => look-back cannot deadlock);
+  // ((u64*)status)[1 + b] = flag << 62 | value of logical CTA b.
+  if (tid == 0) s_block = atomicAdd(&status[0], 1u);
+  __syncthreads();
+  const uint32_t b = s_block;
+  uint64_t* st = reinterpret_cast<uint64_t*>(status) + 1;
+  const int64_t base = (int64_t)b * kEmitThreads;
+  const int64_t i = base + tid;
+  uint32_t c = 0;
   if (i < n) {
     const uint32_t g = perm ? perm[i] : (uint32_t)i;
-    off = offsets[i];
-    s_gid[threadIdx.x] = g;
-    s_low[threadIdx.x] = kCombined ? g : depth_key[g];
-    s_rect[threadIdx.x] = rect[g];
+    c = count[g];
+    s_gid[tid] = g;
+    s_low[tid] = kCombined ? g : depth_key[g];
+    s_rect[tid] = rect[g];
   }
-  const uint32_t k_total = *total;
-  s_off[threadIdx.x] = (i < n) ? off : k_total;
-  if (threadIdx.x == 0) {
-    const int64_t nxt = base + kEmitThreads;
-    s_off[kEmitThreads] = (nxt < n) ? offsets[nxt] : k_total;
+  uint32_t inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint32_t warp_off = 0, block_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kEmitThreads / 32; ++w) {
+    const uint32_t t = s_warp[w];
+    if (w < warp) warp_off += t;
+    block_sum += t;
+  }
+  if (warp == 0) {
+    constexpr uint64_t kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
+    uint64_t excl = 0;
+    if (b == 0) {
+      if (lane == 0) st_relaxed64(&st[0], kPre | (uint64_t)block_sum);
+    } else {
+      if (lane == 0) st_relaxed64(&st[b], kAgg | (uint64_t)block_sum);
+      for (int64_t idx = (int64_t)b - 1;; idx -= 32) {  // a window of 32 predecessors per round
+        const int64_t j = idx - lane;
+        uint64_t sv = kPre;  // virtual CTA -1: inclusive prefix 0
+        if (j >= 0) {
+          sv = ld_relaxed64(&st[j]);
+          while ((sv >> 62) == 0) sv = ld_relaxed64(&st[j]);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (sv >> 62) == 2u);
+        uint64_t contrib = sv & kMask;
+        if (pm && lane > __ffs(pm) - 1) contrib = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (pm) break;
+      }
+      if (lane == 0) st_relaxed64(&st[b], kPre | ((excl + block_sum) & kMask));
+    }
+    if (lane == 0) s_excl = (uint32_t)excl;
+  }
+  __syncthreads();
+  s_off[tid] = s_excl + warp_off + inc - c;
+  if (tid == 0) s_off[kEmitThreads] = s_excl + block_sum;
   __syncthreads();
   const uint32_t begin = s_off[0], end = s_off[kEmitThreads];
   for (uint32_t o4 = (begin & ~3u) + 4u * threadIdx.x; o4 < end; o4 += 4u * kEmitThreads) {
@@ -241,15 +189,14 @@ emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ p
   }
 }
 
-int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
-                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
-                uint32_t* payload, cudaStream_t st) {
+int launch_emit(const uint32_t* count, const uint32_t* perm, int64_t n, const uint32_t* depth_key, const ushort4* rect,
+                int tiles_x, bool combined, uint64_t* keys, uint32_t* payload, uint32_t* status, cudaStream_t st) {
   if (n == 0) return 0;
   unsigned blocks = (unsigned)((n + kEmitThreads - 1) / kEmitThreads);
   if (combined)
-    emit_kernel<true><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
+    emit_kernel<true><<<blocks, kEmitThreads, 0, st>>>(count, perm, n, depth_key, rect, tiles_x, keys, payload, status);
   else
-    emit_kernel<false><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
+    emit_kernel<false><<<blocks, kEmitThreads, 0, st>>>(count, perm, n, depth_key, rect, tiles_x, keys, payload, status);
   return (int)cudaGetLastError();
 }
 
@@ -467,7 +414,8 @@ constexpr int kStatThreads = 1024;
 
 __global__ void __launch_bounds__(kStatThreads)
 tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, int tiles_y,
-                  uint32_t* __restrict__ tile_hist, uint2* __restrict__ ranges, uint32_t* __restrict__ k_total) {
+                  uint32_t* __restrict__ tile_hist, uint2* __restrict__ ranges, uint32_t* __restrict__ k_total,
+                  const uint32_t* __restrict__ m_counter, volatile uint32_t* host_mailbox, uint32_t seq) {
   extern __shared__ int32_t s_grid[];
   __shared__ uint32_t s_hist[4][kRadix];
   __shared__ uint32_t s_warp[kStatThreads / 32];
@@ -569,11 +517,20 @@ tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, 
   if (tid == 0) {  // 64-bit total: the host rejects K >= 2^32 (positions are u32)
     k_total[0] = (uint32_t)total64;
     k_total[1] = (uint32_t)(total64 >> 32);
+    if (host_mailbox) {
+      // Mailbox in mapped pinned host memory: the host polls word 4 and learns M and K while the depth sort is
+      // still running on the main stream, so the read-back it needs to size the key buffers costs no bubble.
+      host_mailbox[0] = *m_counter;
+      host_mailbox[2] = (uint32_t)total64;
+      host_mailbox[3] = (uint32_t)(total64 >> 32);
+      __threadfence_system();
+      host_mailbox[4] = seq;
+    }
   }
 }
 
 int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,
-                      cudaStream_t st) {
+                      const uint32_t* m_counter, uint32_t* host_mailbox, uint32_t seq, cudaStream_t st) {
   if (geom.tiles_x <= 0 || geom.tiles_y <= 0) return 0;
   const size_t bytes = (size_t)(geom.tiles_x + 1) * (size_t)(geom.tiles_y + 1) * sizeof(int32_t);
   const int use_smem = bytes <= 200 * 1024;
@@ -582,7 +539,7 @@ int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, u
     if (e != cudaSuccess) return (int)e;
   }
   tile_stats_kernel<<<1, kStatThreads, use_smem ? bytes : 0, st>>>(diff_grid, use_smem, geom.tiles_x, geom.tiles_y,
-                                                                  tile_hist, ranges, k_total);
+                                                                  tile_hist, ranges, k_total, m_counter, host_mailbox, seq);
   return (int)cudaGetLastError();
 }
 

@@ -59,7 +59,7 @@ int ceil_log2(int64_t v) {
 
 // control block, zeroed once per frame:
 //   [hdr 16: 0 = M, 1 = K mod 2^32 (scan), 2-3 = K (tile grid, 64-bit)] [hist 8 x 256: rows 0-3 depth digits, 4-7 tile digits]
-//   [difference grid (tiles_x+1)*(tiles_y+1)] [scan look-back status] [depth-sort tickets + status]
+//   [difference grid (tiles_x+1)*(tiles_y+1)] [tile cursors (BINNED)] [emit scan status] [depth-sort tickets + status]
 constexpr int kCtlHeaderWords = 16;
 constexpr int kCtlHistWords = kMaxPasses * kRadix;
 
@@ -73,7 +73,7 @@ CtlLayout ctl_layout(FrameGeom g, int64_t n_rows, size_t dsort_words) {
   L.grid = L.hist + kCtlHistWords;
   L.cursor = up4(L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1));  // BINNED: one fill cursor per tile
   L.scan = up4(L.cursor + (size_t)g.tiles_x * (size_t)g.tiles_y);
-  L.dsort = up4(L.scan + scan_status_words(n_rows));
+  L.dsort = up4(L.scan + emit_status_words(n_rows));
   L.total = up4(L.dsort + dsort_words);
   return L;
 }
@@ -85,14 +85,18 @@ struct GsbContext {
   int64_t n = 0, n_pad = 0;
   DevBuf planes, staging;
   // per-Gaussian frame data
-  DevBuf depth_key, rec, rect, count, offsets, bbox;
+  DevBuf depth_key, rec, rect, count, bbox;
   DevBuf dbg_cov2d, dbg_conic, dbg_bbox;
   DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, rank;
   // per-instance
   DevBuf keys_a, keys_b, vals_a, vals_b;
   DevBuf ranges, control, control2;
   DevBuf image, image2, scratch;
-  uint32_t* pinned = nullptr;  // [0]=M, [1]=K
+  uint32_t* pinned = nullptr;  // mailbox written by tile_stats_kernel: [0]=M, [2..3]=K, [4]=frame sequence number
+  uint32_t* pinned_dev = nullptr;  // device alias of the mailbox
+  uint32_t seq = 0;
+  cudaStream_t aux = nullptr;   // side stream for work that is off the critical path (tile stats)
+  cudaEvent_t ev_fork = nullptr, ev_stats = nullptr;
   // state of the last frame
   bool have_frame = false;
   bool sorted_in_a = true;
@@ -138,6 +142,43 @@ int check_params(const GsbCamera* cam, const GsbParams* prm) {
   return GSB_OK;
 }
 
+// tile_stats_kernel needs only the projection's difference grid, not the depth sort: run it on the context's
+// auxiliary stream so that it overlaps the (latency-bound) depth-sort passes; the main stream joins on ev_stats.
+int launch_stats_async(GsbContext* c, FrameGeom geom, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, int* launches) {
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
+  GSB_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+  GSB_CUDA_TRY(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+  ++c->seq;
+  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom, ctl + L.hist + 4 * kRadix,
+                                              c->ranges.as<uint2>(), ctl + 2, ctl, c->pinned_dev, c->seq, c->aux));
+  if (tiles > 0) ++*launches;
+  GSB_CUDA_TRY(cudaEventRecord(c->ev_stats, c->aux));
+  return GSB_OK;
+}
+
+// Wait for tile_stats_kernel's mailbox (M, K) without draining the main stream: the depth-sort passes queued
+// behind the projection keep running while the host sizes the key buffers and queues emit / sort / composite.
+int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t st, int64_t* m, int64_t* k) {
+  if (tiles <= 0) {  // no tile grid, no tile_stats launch: plain read-back of M, K = 0
+    GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 4, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));
+    *m = c->pinned[0]; *k = 0;
+    return GSB_OK;
+  }
+  volatile uint32_t* box = c->pinned;
+  for (uint64_t spins = 0; box[4] != c->seq; ++spins) {
+    if ((spins & 0x3FFF) == 0x3FFF) {
+      cudaError_t q = cudaStreamQuery(c->aux);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
+      if (q == cudaSuccess && box[4] != c->seq) return GSB_E_INTERNAL;  // kernel finished, mailbox never written
+    }
+  }
+  *m = box[0];
+  *k = (int64_t)(((uint64_t)box[3] << 32) | box[2]);
+  return GSB_OK;
+}
+
 // depth sort of the per-Gaussian keys (N items): leaves the order in ord_vals_{a|b}.  The first pass reads
 // depth_key directly and synthesises payload = index; `hist` = the 4 depth-digit histograms (unweighted).
 int depth_sort(GsbContext* c, int64_t n, const uint32_t* hist, uint32_t* control_words, cudaStream_t st, int* launches,
@@ -163,24 +204,12 @@ int depth_sort(GsbContext* c, int64_t n, const uint32_t* hist, uint32_t* control
 int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, FrameGeom geom,
                  uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
-  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
-  GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
-  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl + 1,
-                                        ctl + L.scan, st));
-  ++*launches;
-  tm.mark(GSB_STAGE_SCAN);
-  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom, ctl + L.hist + 4 * kRadix,
-                                              c->ranges.as<uint2>(), ctl + 2, st));
-  if (tiles > 0) ++*launches;
-  tm.mark(GSB_STAGE_RANGES);
-  // the one host round trip of the frame: M and K
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 16, cudaMemcpyDeviceToHost, st));
-  GSB_CUDA_TRY(cudaStreamSynchronize(st));
-  const int64_t m = c->pinned[0];
-  const int64_t k64 = tiles > 0 ? (int64_t)(((uint64_t)c->pinned[3] << 32) | c->pinned[2]) : 0;
-  if (k64 >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;         // payload positions and ranges are u32
-  const int64_t k = k64;
-  if (tiles > 0 && (int64_t)c->pinned[1] != k) return GSB_E_INTERNAL;  // scan and tile grid must agree
+  // tile stats were launched on the auxiliary stream right after the projection (they do not depend on the
+  // depth sort); join them here, then the one host round trip of the frame: M and K
+  int64_t m = 0, k = 0;
+  GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k));
+  GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // ranges / tile histograms are inputs of what follows
+  if (k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
   c->info.m_in_view = m;
   c->info.k_instances = k;
 
@@ -196,9 +225,9 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
 
   plan.keys_only = low_bits_sorted ? 1 : 0;
-  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 1, n_rows, c->depth_key.as<uint32_t>(),
+  GSB_CUDA_TRY((cudaError_t)launch_emit(c->count.as<uint32_t>(), perm, n_rows, c->depth_key.as<uint32_t>(),
                                         c->rect.as<ushort4>(), geom.tiles_x, /*combined=*/low_bits_sorted,
-                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
+                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), ctl + L.scan, st));
   ++*launches;
   tm.mark(GSB_STAGE_EMIT);
   bool in_a = true;
@@ -219,15 +248,9 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
 int bin_by_tile(GsbContext* c, int64_t n_rows, const uint32_t* order, FrameGeom geom, uint32_t* ctl, const CtlLayout& L,
                 cudaStream_t st, StageTimer& tm, int* launches) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
-  GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
-  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom, ctl + L.hist + 4 * kRadix,
-                                              c->ranges.as<uint2>(), ctl + 2, st));
-  if (tiles > 0) ++*launches;
-  tm.mark(GSB_STAGE_RANGES);
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 16, cudaMemcpyDeviceToHost, st));
-  GSB_CUDA_TRY(cudaStreamSynchronize(st));  // the one host round trip of the frame: M and K
-  const int64_t m = c->pinned[0];
-  const int64_t k = tiles > 0 ? (int64_t)(((uint64_t)c->pinned[3] << 32) | c->pinned[2]) : 0;
+  int64_t m = 0, k = 0;
+  GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k));
+  GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // tile stats ran on the auxiliary stream
   if (k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
   c->info.m_in_view = m;
   c->info.k_instances = k;
@@ -304,6 +327,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
                                            reinterpret_cast<int32_t*>(ctl + L.grid), nullptr, st));
   if (n > 0) ++launches;
   tm.mark(GSB_STAGE_PROJECT);
+  GSB_TRY(launch_stats_async(c, geom, ctl, L, st, &launches));
   const uint32_t* perm = nullptr;
   if (split && n > 0) {
     int dp = 0;
@@ -389,7 +413,15 @@ int gsb_create(GsbContext** out, int device) {
     e = std::getenv("GSB_FORCE_WIDE_STATUS");             // 1: 64-bit look-back words even below 2^30 keys
     set_force_wide_status(e ? std::atoi(e) : 0);
   }
-  if (cudaMallocHost((void**)&c->pinned, 64) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
+  if (cudaHostAlloc((void**)&c->pinned, 64, cudaHostAllocMapped) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
+  std::memset(c->pinned, 0, 64);
+  if (cudaHostGetDevicePointer((void**)&c->pinned_dev, c->pinned, 0) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }
+  if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming) != cudaSuccess) {
+    gsb_destroy(c);
+    return GSB_E_ALLOC;
+  }
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }
   *out = c;
@@ -400,12 +432,15 @@ void gsb_destroy(GsbContext* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->offsets, &c->bbox,
+  DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->bbox,
                     &c->dbg_cov2d, &c->dbg_conic, &c->dbg_bbox, &c->ord_keys_a, &c->ord_keys_b, &c->ord_vals_a,
                     &c->ord_vals_b, &c->rank, &c->keys_a, &c->keys_b, &c->vals_a, &c->vals_b, &c->ranges, &c->control,
                     &c->control2, &c->image, &c->image2, &c->scratch};
   for (DevBuf* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_stats) cudaEventDestroy(c->ev_stats);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   delete c;
@@ -608,6 +643,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
                                                        reinterpret_cast<int32_t*>(hdr + L.grid), st));
   if (m > 0) ++launches;
   tm.mark(GSB_STAGE_PROJECT);
+  GSB_TRY(launch_stats_async(c, geom, hdr, L, st, &launches));
   GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, geom, hdr, L, st, tm, &launches));
   c->info.m_in_view = m;
 
