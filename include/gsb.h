@@ -83,6 +83,9 @@ typedef struct GsbParams {
                           splat/gaussian_scene.py:208,:214); 1: ceil(W/T) x ceil(H/T) tiles */
   int32_t sort_mode;   /* GSB_SORT_* */
   int32_t collect_stage_times; /* 1: record CUDA events per stage (adds event overhead) */
+  int32_t async_host_copy; /* 1: when the output pointer is HOST memory, copy the image on the context's copy
+                              stream so that it overlaps the next frame; the host buffer is valid only after
+                              gsb_join_host_copies(ctx, stream) + a synchronisation of that stream */
 } GsbParams;
 
 /* Stage indices for gsb_stage_times */
@@ -131,6 +134,11 @@ int gsb_upload(GsbContext* ctx, int64_t n, const float* xyz, const float* scales
  * the key buffers (the tile-instance count K is data dependent). */
 int gsb_render(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, float* out_image,
                void* stream);
+
+/* Makes `stream` wait for every device->host image copy still in flight on the context's copy stream (see
+ * GsbParams.async_host_copy).  After this call, work queued on `stream` -- or a synchronisation of it -- is
+ * ordered after those copies. */
+int gsb_join_host_copies(GsbContext* ctx, void* stream);
 
 /* Same frame, egress variants: (W,H,3) layout of the reference CPU
  * path (image[x][y][c], splat/gaussian_scene.py:206,:227), or 8-bit (H,W,3) clamp(v,0,1)*255. */

@@ -57,40 +57,41 @@ __device__ __forceinline__ void st_relaxed64(uint64_t* p, uint64_t v) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
-// u32 words of status memory for emit's fused scan: a ticket (2 words) + one 64-bit word per CTA
-size_t emit_status_words(int64_t n) { return 2 * ((size_t)((n + kEmitThreads - 1) / kEmitThreads) + 2); }
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of the tile counts in emission order: single pass, decoupled look-back, 8 192 items per CTA
+// (about 120 CTAs at N = 1 M, so the prefix ripples through the grid in 4 window rounds; fusing the scan into
+// emit_kernel's 3 900 CTAs was measured 20 us slower).  status[0] = ticket, ((u64*)status)[1 + b] = flag << 62
+// | value of logical CTA b; 64-bit words because K may need more than the 30 bits a u32 leaves next to the flags.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
 
-template <bool kCombined>
-__global__ void __launch_bounds__(kEmitThreads)
-emit_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
-            const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
-            uint64_t* __restrict__ keys, uint32_t* __restrict__ payload, uint32_t* status) {
-  __shared__ uint32_t s_off[kEmitThreads + 1];
-  __shared__ uint32_t s_gid[kEmitThreads];
-  __shared__ uint32_t s_low[kEmitThreads];  // low key word: depth bits (FULL) or Gaussian index (SPLIT)
-  __shared__ ushort4 s_rect[kEmitThreads];
+size_t scan_status_words(int64_t n) { return 2 * ((size_t)((n + kScanTile - 1) / kScanTile) + 2); }
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
+            uint32_t* __restrict__ offsets, uint32_t* status) {
+  constexpr uint64_t kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
   __shared__ uint32_t s_block, s_excl;
-  __shared__ uint32_t s_warp[kEmitThreads / 32];
+  __shared__ uint32_t s_warp[kScanThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // ---- fused exclusive scan of the tile counts in emission order (single pass, decoupled look-back) ----
-  // status[0] = ticket (logical CTA order == launch order of the predecessors => look-back cannot deadlock);
-  // ((u64*)status)[1 + b] = flag << 62 | value of logical CTA b.
-  if (tid == 0) s_block = atomicAdd(&status[0], 1u);
+  if (tid == 0) s_block = atomicAdd(&status[0], 1u);  // ticket: predecessors are already running
   __syncthreads();
   const uint32_t b = s_block;
   uint64_t* st = reinterpret_cast<uint64_t*>(status) + 1;
-  const int64_t base = (int64_t)b * kEmitThreads;
-  const int64_t i = base + tid;
-  uint32_t c = 0;
-  if (i < n) {
-    const uint32_t g = perm ? perm[i] : (uint32_t)i;
-    c = count[g];
-    s_gid[tid] = g;
-    s_low[tid] = kCombined ? g : depth_key[g];
-    s_rect[tid] = rect[g];
+  const int64_t base = (int64_t)b * kScanTile + (int64_t)tid * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t local = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k;
+    uint32_t c = 0;
+    if (i < n) c = perm ? count[perm[i]] : count[i];
+    v[k] = local;  // exclusive within the thread
+    local += c;
   }
-  uint32_t inc = c;
+  uint32_t inc = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -99,14 +100,12 @@ emit_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
   uint32_t warp_off = 0, block_sum = 0;
-#pragma unroll
-  for (int w = 0; w < kEmitThreads / 32; ++w) {
+  for (int w = 0; w < kScanThreads / 32; ++w) {
     const uint32_t t = s_warp[w];
     if (w < warp) warp_off += t;
     block_sum += t;
   }
   if (warp == 0) {
-    constexpr uint64_t kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
     uint64_t excl = 0;
     if (b == 0) {
       if (lane == 0) st_relaxed64(&st[0], kPre | (uint64_t)block_sum);
@@ -132,8 +131,46 @@ emit_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
     if (lane == 0) s_excl = (uint32_t)excl;
   }
   __syncthreads();
-  s_off[tid] = s_excl + warp_off + inc - c;
-  if (tid == 0) s_off[kEmitThreads] = s_excl + block_sum;
+  const uint32_t off = s_excl + warp_off + inc - local;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k;
+    if (i < n) offsets[i] = off + v[k];
+  }
+}
+
+int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* status,
+                cudaStream_t st) {
+  if (n == 0) return 0;
+  scan_kernel<<<(unsigned)((n + kScanTile - 1) / kScanTile), kScanThreads, 0, st>>>(count, perm, n, offsets, status);
+  return (int)cudaGetLastError();
+}
+
+template <bool kCombined>
+__global__ void __launch_bounds__(kEmitThreads)
+emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
+            int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
+            uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  __shared__ uint32_t s_off[kEmitThreads + 1];
+  __shared__ uint32_t s_gid[kEmitThreads];
+  __shared__ uint32_t s_low[kEmitThreads];  // low key word: depth bits (FULL) or Gaussian index (SPLIT)
+  __shared__ ushort4 s_rect[kEmitThreads];
+  const int64_t base = (int64_t)blockIdx.x * kEmitThreads;
+  const int64_t i = base + threadIdx.x;
+  uint32_t off = 0;
+  if (i < n) {
+    const uint32_t g = perm ? perm[i] : (uint32_t)i;
+    off = offsets[i];
+    s_gid[threadIdx.x] = g;
+    s_low[threadIdx.x] = kCombined ? g : depth_key[g];
+    s_rect[threadIdx.x] = rect[g];
+  }
+  const uint32_t k_total = *total;
+  s_off[threadIdx.x] = (i < n) ? off : k_total;
+  if (threadIdx.x == 0) {
+    const int64_t nxt = base + kEmitThreads;
+    s_off[kEmitThreads] = (nxt < n) ? offsets[nxt] : k_total;
+  }
   __syncthreads();
   const uint32_t begin = s_off[0], end = s_off[kEmitThreads];
   for (uint32_t o4 = (begin & ~3u) + 4u * threadIdx.x; o4 < end; o4 += 4u * kEmitThreads) {
@@ -189,14 +226,15 @@ emit_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
   }
 }
 
-int launch_emit(const uint32_t* count, const uint32_t* perm, int64_t n, const uint32_t* depth_key, const ushort4* rect,
-                int tiles_x, bool combined, uint64_t* keys, uint32_t* payload, uint32_t* status, cudaStream_t st) {
+int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
+                uint32_t* payload, cudaStream_t st) {
   if (n == 0) return 0;
   unsigned blocks = (unsigned)((n + kEmitThreads - 1) / kEmitThreads);
   if (combined)
-    emit_kernel<true><<<blocks, kEmitThreads, 0, st>>>(count, perm, n, depth_key, rect, tiles_x, keys, payload, status);
+    emit_kernel<true><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
   else
-    emit_kernel<false><<<blocks, kEmitThreads, 0, st>>>(count, perm, n, depth_key, rect, tiles_x, keys, payload, status);
+    emit_kernel<false><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
   return (int)cudaGetLastError();
 }
 

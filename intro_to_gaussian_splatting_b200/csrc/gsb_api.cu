@@ -73,7 +73,7 @@ CtlLayout ctl_layout(FrameGeom g, int64_t n_rows, size_t dsort_words) {
   L.grid = L.hist + kCtlHistWords;
   L.cursor = up4(L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1));  // BINNED: one fill cursor per tile
   L.scan = up4(L.cursor + (size_t)g.tiles_x * (size_t)g.tiles_y);
-  L.dsort = up4(L.scan + emit_status_words(n_rows));
+  L.dsort = up4(L.scan + scan_status_words(n_rows));
   L.total = up4(L.dsort + dsort_words);
   return L;
 }
@@ -85,7 +85,7 @@ struct GsbContext {
   int64_t n = 0, n_pad = 0;
   DevBuf planes, staging;
   // per-Gaussian frame data
-  DevBuf depth_key, rec, rect, count, bbox;
+  DevBuf depth_key, rec, rect, count, offsets, bbox;
   DevBuf dbg_cov2d, dbg_conic, dbg_bbox;
   DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, rank;
   // per-instance
@@ -97,6 +97,12 @@ struct GsbContext {
   uint32_t seq = 0;
   cudaStream_t aux = nullptr;   // side stream for work that is off the critical path (tile stats)
   cudaEvent_t ev_fork = nullptr, ev_stats = nullptr;
+  // asynchronous image egress: two device staging images, a copy stream, one event per staging image
+  cudaStream_t copy = nullptr;
+  DevBuf host_stage[2];
+  cudaEvent_t ev_rendered = nullptr, ev_copied[2] = {nullptr, nullptr};
+  bool copy_pending[2] = {false, false};
+  int stage_next = 0;
   // state of the last frame
   bool have_frame = false;
   bool sorted_in_a = true;
@@ -204,8 +210,12 @@ int depth_sort(GsbContext* c, int64_t n, const uint32_t* hist, uint32_t* control
 int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, FrameGeom geom,
                  uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
+  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl + L.scan, st));
+  if (n_rows > 0) ++*launches;
+  tm.mark(GSB_STAGE_SCAN);
   // tile stats were launched on the auxiliary stream right after the projection (they do not depend on the
-  // depth sort); join them here, then the one host round trip of the frame: M and K
+  // depth sort) and post M and K to the host mailbox; pick them up without draining the main stream
   int64_t m = 0, k = 0;
   GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k));
   GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // ranges / tile histograms are inputs of what follows
@@ -225,9 +235,9 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
 
   plan.keys_only = low_bits_sorted ? 1 : 0;
-  GSB_CUDA_TRY((cudaError_t)launch_emit(c->count.as<uint32_t>(), perm, n_rows, c->depth_key.as<uint32_t>(),
+  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 2, n_rows, c->depth_key.as<uint32_t>(),
                                         c->rect.as<ushort4>(), geom.tiles_x, /*combined=*/low_bits_sorted,
-                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), ctl + L.scan, st));
+                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
   ++*launches;
   tm.mark(GSB_STAGE_EMIT);
   bool in_a = true;
@@ -395,6 +405,7 @@ void gsb_default_params(GsbParams* p) {
   p->full_cover = 0;
   p->sort_mode = GSB_SORT_AUTO;
   p->collect_stage_times = 0;
+  p->async_host_copy = 0;
 }
 
 int gsb_create(GsbContext** out, int device) {
@@ -418,7 +429,11 @@ int gsb_create(GsbContext** out, int device) {
   if (cudaHostGetDevicePointer((void**)&c->pinned_dev, c->pinned, 0) != cudaSuccess) { gsb_destroy(c); return GSB_E_ALLOC; }
   if (cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_copied[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_copied[1], cudaEventDisableTiming) != cudaSuccess) {
     gsb_destroy(c);
     return GSB_E_ALLOC;
   }
@@ -432,13 +447,17 @@ void gsb_destroy(GsbContext* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->bbox,
+  DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->offsets, &c->bbox,
                     &c->dbg_cov2d, &c->dbg_conic, &c->dbg_bbox, &c->ord_keys_a, &c->ord_keys_b, &c->ord_vals_a,
                     &c->ord_vals_b, &c->rank, &c->keys_a, &c->keys_b, &c->vals_a, &c->vals_b, &c->ranges, &c->control,
                     &c->control2, &c->image, &c->image2, &c->scratch};
   for (DevBuf* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->copy) cudaStreamDestroy(c->copy);
+  if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
+  for (auto& e : c->ev_copied) if (e) cudaEventDestroy(e);
+  c->host_stage[0].release(); c->host_stage[1].release();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_stats) cudaEventDestroy(c->ev_stats);
   for (auto& e : c->ev)
@@ -481,12 +500,37 @@ int gsb_upload(GsbContext* c, int64_t n, const float* xyz, const float* scales, 
   return GSB_OK;
 }
 
+int gsb_join_host_copies(GsbContext* c, void* stream) {
+  if (!c) return GSB_E_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int b = 0; b < 2; ++b)
+    if (c->copy_pending[b]) {
+      GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copied[b], 0));
+      c->copy_pending[b] = false;
+    }
+  return GSB_OK;
+}
+
 int gsb_render(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float* out_image, void* stream) {
   if (!c || !out_image) return GSB_E_INVALID_ARG;
   GSB_TRY(check_params(cam, prm));
   cudaStream_t st = (cudaStream_t)stream;
   if (is_device_pointer(out_image)) return render_device(c, cam, prm, out_image, st);
   const size_t bytes = (size_t)cam->width * cam->height * 3 * sizeof(float);
+  if (prm->async_host_copy) {
+    // double-buffered staging: frame i is copied to the host on the copy stream while frame i+1 renders
+    const int b = c->stage_next;
+    c->stage_next ^= 1;
+    GSB_TRY(c->host_stage[b].ensure(bytes));
+    if (c->copy_pending[b]) GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copied[b], 0));  // staging image still in flight
+    GSB_TRY(render_device(c, cam, prm, c->host_stage[b].as<float>(), st));
+    GSB_CUDA_TRY(cudaEventRecord(c->ev_rendered, st));
+    GSB_CUDA_TRY(cudaStreamWaitEvent(c->copy, c->ev_rendered, 0));
+    GSB_CUDA_TRY(cudaMemcpyAsync(out_image, c->host_stage[b].p, bytes, cudaMemcpyDeviceToHost, c->copy));
+    GSB_CUDA_TRY(cudaEventRecord(c->ev_copied[b], c->copy));
+    c->copy_pending[b] = true;
+    return GSB_OK;
+  }
   GSB_TRY(c->image.ensure(bytes));
   GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
   GSB_CUDA_TRY(cudaMemcpyAsync(out_image, c->image.p, bytes, cudaMemcpyDeviceToHost, st));

@@ -69,13 +69,16 @@ int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamer
 int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,
                       const uint32_t* m_counter, uint32_t* host_mailbox, uint32_t seq, cudaStream_t st);
 
-// emit (binning.cu): the exclusive scan of count[] in emission order is fused into the kernel (decoupled
-// look-back).  `status` needs emit_status_words(n) zeroed u32 words, 8-byte aligned.
-size_t emit_status_words(int64_t n);
-// combined = false: keys = tile<<32 | depth bits, payload = Gaussian index (FULL mode);
-// combined = true:  keys = tile<<32 | Gaussian index, payload untouched (SPLIT mode, keys-only tile passes)
-int launch_emit(const uint32_t* count, const uint32_t* perm, int64_t n, const uint32_t* depth_key, const ushort4* rect,
-                int tiles_x, bool combined, uint64_t* keys, uint32_t* payload, uint32_t* status, cudaStream_t st);
+// exclusive scan of count[perm ? perm[i] : i] for i < n -> offsets[i] (u32, wraps if K >= 2^32: the host rejects
+// that from tile_stats' 64-bit total).  `status` needs scan_status_words(n) zeroed u32 words, 8-byte aligned.
+size_t scan_status_words(int64_t n);
+int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* status,
+                cudaStream_t st);
+// `total`: device pointer to K (low word).  combined = false: keys = tile<<32 | depth bits, payload = Gaussian
+// index (FULL); combined = true: keys = tile<<32 | Gaussian index, payload untouched (SPLIT, keys-only passes)
+int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
+                uint32_t* payload, cudaStream_t st);
 // debug only: sorted keys tile<<32 | depth bits from ranges + sorted payload (SPLIT mode never stores them)
 int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
                         uint64_t* keys, cudaStream_t st);

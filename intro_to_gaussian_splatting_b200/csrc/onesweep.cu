@@ -315,7 +315,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
 }
 
 template <typename KeyT, int kItems, int kMode, typename W>
-__global__ void __launch_bounds__(kThreads, kItems == 8 ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, kItems == 8 ? 4 : 3)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                 const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,

@@ -91,6 +91,11 @@ class Rasterizer:
             check(fn(self._h, C.byref(cam), C.byref(params), _ptr(out), self._stream()), "gsb_render")
         return out
 
+    def join_host_copies(self) -> None:
+        """Order the current stream after every asynchronous image copy (params.async_host_copy) still in flight."""
+        with torch.cuda.device(self.device):
+            check(self._lib.gsb_join_host_copies(self._h, self._stream()), "gsb_join_host_copies")
+
     def preprocess(self, cam: GsbCamera, params: Optional[GsbParams] = None, with_source_index: bool = False):
         params = params or _lib.default_params()
         n = self.n

@@ -50,11 +50,12 @@ class Params(C.Structure):
         ("full_cover", C.c_int32),
         ("sort_mode", C.c_int32),
         ("collect_stage_times", C.c_int32),
+        ("async_host_copy", C.c_int32),
     ]
 
 
 def default_params(**over) -> Params:
-    p = Params(16, 0.2, 1.3, 1e-3, 0.1, 3.0, 1e-6, 0.99, 0, 0, 0, 0)
+    p = Params(16, 0.2, 1.3, 1e-3, 0.1, 3.0, 1e-6, 0.99, 0, 0, 0, 0, 0)
     for k, v in over.items():
         setattr(p, k, v)
     return p

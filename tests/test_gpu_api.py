@@ -98,3 +98,25 @@ def test_errors_are_runtime_errors():
     with pytest.raises(RuntimeError):  # mixed devices, like torch::checkAllSameGPU
         ext.render_image(64, 64, 16, pp.points.cpu(), pp.colors, pp.inverse_covariance_2d, pp.min_x, pp.max_x,
                          pp.min_y, pp.max_y, pp.sigmoid_opacity)
+
+
+def test_async_host_copy_matches_synchronous_render():
+    """params.async_host_copy: frame i's D2H copy overlaps frame i+1; after join + synchronise the pinned host
+    images equal the synchronously rendered ones, also when the two staging images are recycled."""
+    from intro_to_gaussian_splatting_b200 import Rasterizer
+    from helpers import scene_arrays
+    sc, images, _ = scene_and_images("small", n_views=4)
+    r = Rasterizer(0)
+    try:
+        r.upload(*[a.cuda() for a in scene_arrays(sc)])
+        ref = [r.render(images[i].pack(), _lib.default_params()).cpu() for i in (1, 2, 3, 4)]
+        hosts = [torch.empty((96, 160, 3), dtype=torch.float32).pin_memory() for _ in range(4)]
+        prm = _lib.default_params(async_host_copy=1)
+        for k, i in enumerate((1, 2, 3, 4)):
+            r.render(images[i].pack(), prm, out=hosts[k])
+        r.join_host_copies()
+        torch.cuda.synchronize()
+        for k in range(4):
+            assert torch.equal(hosts[k], ref[k]), k
+    finally:
+        r.close()
