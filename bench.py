@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--full-cover", type=int, default=1)
     ap.add_argument("--sort-mode", default="auto", choices=["auto", "full", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="frames in flight per GPU (one rasterizer context + one CUDA stream each); 1 = strictly serial frames")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     return ap.parse_args()
 
@@ -80,7 +82,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="gsb_clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -258,24 +260,34 @@ def run_ours(args):
     torch.cuda.synchronize()
     bcast_s = time.perf_counter() - t0
 
-    rast = Rasterizer(local)
-    rast.upload(*arrays)
+    F = max(1, args.inflight)
+    rasts = [Rasterizer(local) for _ in range(F)]  # independent contexts: own scratch, own aux/copy streams
+    for r_ in rasts:
+        r_.upload(*arrays)
+    rast = rasts[0]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(F)]
     sort_mode = {"auto": _lib.GSB_SORT_AUTO, "full": _lib.GSB_SORT_FULL, "split": _lib.GSB_SORT_SPLIT}[args.sort_mode]
     prm = _lib.default_params(full_cover=args.full_cover, sort_mode=sort_mode)
     prm_t = _lib.default_params(full_cover=args.full_cover, sort_mode=sort_mode, collect_stage_times=1)
+    prm_a = _lib.default_params(full_cover=args.full_cover, sort_mode=sort_mode, async_host_copy=1)
     shard = ViewShard(world, rank, ORBIT)
     views = [shard.view_of_step(s) for s in range(K)]
     H, Wd = spec.height, spec.width
     img = torch.empty((H, Wd, 3), dtype=torch.float32, device=dev)
-    host_img = torch.empty((H, Wd, 3), dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    imgs = [img] + [torch.empty_like(img) for _ in range(F - 1)]
+    hosts = [torch.empty((H, Wd, 3), dtype=torch.float32).pin_memory() for _ in range(2 * F)]
+    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=dev) for _ in range(F)]
+    flush = flushes[0]
 
-    # warm-up (>= 3 frames) + one untimed sweep over the timed views: scratch reaches its final size
+    # warm-up (>= 3 frames) + one untimed sweep over the timed views: scratch reaches its final size in every context
     for s in range(W):
-        rast.render(cams[shard.view_of_step(K + s)], prm, out=img)
-    for v in views:
-        rast.render(cams[v], prm, out=img)
-        rast.render(cams[v], prm, out=host_img)
+        for f in range(F):
+            rasts[f].render(cams[shard.view_of_step(K + s)], prm, out=imgs[f])
+    for s, v in enumerate(views):
+        for f in range(F):
+            rasts[f].render(cams[v], prm, out=imgs[f])
+            rasts[f].render(cams[v], prm_a, out=hosts[f])
+            rasts[f].join_host_copies()
     torch.cuda.synchronize()
 
     def barrier():
@@ -283,50 +295,60 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(out, params):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    def pipelined_loop(outs, params, join, do_flush=False):
+        """K frames, F in flight: frame s runs in context s % F on stream s % F (each context holds its OWN copy of the
+        Gaussian set, so with F >= 3 the inputs cycled through are larger than L2: 3 x 56 MB > 126 MB); one event pair
+        on the main stream brackets the whole loop (the side streams fork from the start event and are joined before
+        the end event).  do_flush additionally writes 256 MiB before every frame INSIDE the timed region.
+        Returns total ms, kernel launches, frame infos."""
+        main = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done = [torch.cuda.Event() for _ in range(F)]
         launches = 0
         infos = []
         barrier()
+        e0.record(main)
+        for st_ in streams:
+            st_.wait_event(e0)
         for s, v in enumerate(views):
-            flush.zero_()  # L2 flush, outside the per-frame events
-            ev[s][0].record()
-            rast.render(cams[v], params, out=out)
-            ev[s][1].record()
-            info = rast.frame_info()
+            f = s % F
+            with torch.cuda.stream(streams[f]):
+                if do_flush:
+                    flushes[f].zero_()
+                rasts[f].render(cams[v], params, out=outs[s % len(outs)])
+            info = rasts[f].frame_info()
             launches += info.kernel_launches
             infos.append(info)
+        for f in range(F):
+            with torch.cuda.stream(streams[f]):
+                if join:
+                    rasts[f].join_host_copies()
+                done[f].record(streams[f])
+            main.wait_event(done[f])
+        e1.record(main)
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        return ms, launches, infos
-
-    def e2e_loop():
-        """End to end through the public API with HOST buffers: host camera/params structs in, the fp32 image
-        copied to pinned host memory every frame (asynchronous egress: the copy of frame i overlaps frame i+1 on
-        the context's copy stream; the loop ends with a join + synchronise).  The L2 flush sits INSIDE this timed
-        region (it costs ~40 us per frame), one event pair brackets the whole loop."""
-        hosts = [host_img, torch.empty_like(host_img).pin_memory()]
-        prm_a = _lib.default_params(full_cover=args.full_cover, sort_mode=sort_mode, async_host_copy=1)
-        for s, v in enumerate(views[:2]):  # warm the staging images
-            rast.render(cams[v], prm_a, out=hosts[s % 2])
-        rast.join_host_copies()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for s, v in enumerate(views):
-            flush.zero_()
-            rast.render(cams[v], prm_a, out=hosts[s % 2])
-        rast.join_host_copies()
-        e1.record()
-        barrier()
-        return e0.elapsed_time(e1)
+        return e0.elapsed_time(e1), launches, infos
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, infos = timed_loop(img, prm)          # inputs resident, output stays in HBM
-    ms_e2e = e2e_loop()                                    # host structs in, image to pinned host memory
+    explicit_flush = F < 3  # fewer than 3 scene copies do not exceed L2: fall back to flushing inside the region
+    pipelined_loop(imgs, prm, join=False)                             # untimed pass: clocks in steady state
+    ms_dev, launches, infos = pipelined_loop(imgs, prm, join=False, do_flush=explicit_flush)
+    ms_e2e, _, _ = pipelined_loop(hosts, prm_a, join=True, do_flush=explicit_flush)
+    pipelined_loop(imgs, prm, join=False, do_flush=True)                       # untimed pass of the flush variant
+    ms_dev_flush, _, _ = pipelined_loop(imgs, prm, join=False, do_flush=True)  # same loop, 256 MiB written per frame
     clocks = sampler.stop() if rank == 0 else None
+
+    # single-frame latency (serial frames, flush outside the events), for reference next to the throughput
+    lat_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for s, v in enumerate(views):
+        flush.zero_()
+        lat_ev[s][0].record()
+        rast.render(cams[v], prm, out=img)
+        lat_ev[s][1].record()
+    torch.cuda.synchronize()
+    frame_latency_ms = sum(a.elapsed_time(b) for a, b in lat_ev) / K
 
     # per-stage times for the roofline (separate loop: the event pairs add a little overhead)
     stage_ms = {k: 0.0 for k in _lib.STAGE_NAMES}
@@ -341,10 +363,10 @@ def run_ours(args):
             stage_ms[k] += t
     stage_ms = {k: t / K for k, t in stage_ms.items()}
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_e2e, ms_dev_flush], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev_max, ms_e2e_max = float(t[0]), float(t[1])
+    ms_dev_max, ms_e2e_max, ms_flush_max = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -390,15 +412,21 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": workload_name(spec), "full_cover": args.full_cover, "tile_size": 16, "semantics": "ref_cpu",
                    "sort_mode": "split" if split else "full", "views_per_rank": K, "parallelism": f"view-sharded x{world}",
-                   "l2": "flushed between timed frames (256 MiB memset, outside the per-frame events)",
+                   "frames_in_flight": F,
+                   "l2": ("256 MiB written before every frame, inside the timed region" if explicit_flush else
+                          f"inputs larger than L2: {F} contexts, each with its own {56 * spec.n / 1e6:.0f} MB copy of the "
+                          f"Gaussian set, used round-robin ({F * 56 * spec.n / 1e6:.0f} MB > 126 MB L2); each frame also "
+                          "streams ~0.4 GB of intermediates; no explicit flush"),
+                   "value_with_flush_inside_timed_region": round(K * world / (ms_flush_max * 1e-3), 1),
+                   "frame_latency_ms_serial": round(frame_latency_ms, 4),
                    "mean_in_view": round(mean_m), "mean_tile_instances": round(mean_k),
                    "gaussian_broadcast_s": round(bcast_s, 4)},
         "e2e": {"value": K * world / (ms_e2e_max * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_max / K,
                 "h2d_bytes_per_step": C.sizeof(_lib.GsbCamera) + C.sizeof(_lib.GsbParams),
                 "d2h_bytes_per_step": H * Wd * 3 * 4 + 8,
                 "note": "gsb_render with host structs in and a pinned host image out (async egress on the copy stream, "
-                        "joined before the end event); the L2 flush is inside this timed region; Gaussians stay "
-                        "resident like model weights"},
+                        "joined before the end event); same pipelined loop as `value`; Gaussians stay resident like "
+                        "model weights"},
         "gpu_launches": launches,
         "launches_per_step": launches / K,
         "roofline": roofline,

@@ -120,3 +120,31 @@ def test_async_host_copy_matches_synchronous_render():
             assert torch.equal(hosts[k], ref[k]), k
     finally:
         r.close()
+
+
+def test_three_contexts_in_flight_match_serial_frames():
+    """bench.py keeps 3 frames in flight (3 contexts, 3 streams).  Frames rendered that way must be bit-identical
+    to the same frames rendered one at a time: the contexts share nothing but the GPU."""
+    from intro_to_gaussian_splatting_b200 import Rasterizer
+    from helpers import scene_arrays
+    sc, images, _ = scene_and_images("cfg2", n_views=6)
+    arrs = [a.cuda() for a in scene_arrays(sc)]
+    rasts = [Rasterizer(0) for _ in range(3)]
+    try:
+        for r in rasts:
+            r.upload(*arrs)
+        prm = _lib.default_params(full_cover=1)
+        serial = [rasts[0].render(images[i + 1].pack(), prm).clone() for i in range(6)]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        outs = [torch.empty_like(serial[0]) for _ in range(6)]
+        for rep in range(3):  # several rounds so that scratch reuse across frames is exercised too
+            for i in range(6):
+                with torch.cuda.stream(streams[i % 3]):
+                    rasts[i % 3].render(images[i + 1].pack(), prm, out=outs[i])
+            torch.cuda.synchronize()
+            for i in range(6):
+                assert torch.equal(outs[i], serial[i]), (rep, i)
+    finally:
+        for r in rasts:
+            r.close()
