@@ -141,7 +141,7 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 // Staging: records are copied global->shared with cp.async (LDGSTS, 3 x 16 B per record, no register
 // staging) into a double buffer, one batch ahead of the blend loop; the payload index of the batch
 // after that is prefetched into a register so the cp.async addresses are ready when the buffer frees.
-// Slots past the end of the list are filled with a null record (opacity 0 => alpha = 0 => exact no-op)
+// Slots past the end of the list are filled with a null record (log2 opacity -inf => alpha = 0 => exact no-op)
 // so the blend loop needs no tail handling.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastThreads = 64;
@@ -182,6 +182,7 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   float r2 = 0.f, g2 = 0.f, b2 = 0.f, r3 = 0.f, g3 = 0.f, b3 = 0.f;
 
   const float4 null0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 null1 = make_float4(0.f, 0.f, -INFINITY, 0.f);  // log2(opacity) = -inf => alpha = 0 => exact no-op
   // stage batch `b` (records b*128 .. b*128+127) into buffer `buf`; idx[] holds this thread's payload indices
   uint32_t idx[kFastPerThread];
   auto load_idx = [&](uint32_t b) {
@@ -199,7 +200,7 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const float4* src = rec + 3 * (size_t)idx[j];
         cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
       } else {
-        dst[0] = null0; dst[1] = null0; dst[2] = null0;
+        dst[0] = null0; dst[1] = null1; dst[2] = null0;
       }
     }
     cp_async_commit();
@@ -235,7 +236,7 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             const float u0 = __fmaf_rn(dy, q1.x, ta_);                                     \
             const float u1 = __fmaf_rn(dy, q1.y, tb_);                                     \
             const float pw = __fadd_rn(__fmul_rn(u0, dx), __fmul_rn(u1, dy));              \
-            const float al = ex2_approx(pw * 1.4426950408889634f) * q1.z;                  \
+            const float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z)); /* q1.z = log2(op) */ \
             const float ta = T * al;                                                       \
             T = T - ta;                                                                    \
             LIVE = LIVE && (T >= minw);                                                    \
@@ -314,10 +315,11 @@ composite_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
   float2 RA = f2(0.f, 0.f), GA = RA, BA = RA, RB = RA, GB = RA, BB = RA;
 
   // register-staged prefetch: this thread's record of the next batch
-  float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, p2 = p0;
+  float4 p0 = make_float4(0, 0, 0, 0), p1 = make_float4(0.f, 0.f, -INFINITY, 0.f), p2 = p0;
   auto fetch = [&](uint32_t b) {
     const uint32_t slot = b * kPkBatch + tid;
-    p0 = make_float4(0, 0, 0, 0); p1 = p0; p2 = p0;  // null record: opacity 0 => alpha 0 => exact no-op
+    p0 = make_float4(0, 0, 0, 0); p2 = p0;
+    p1 = make_float4(0.f, 0.f, -INFINITY, 0.f);  // null record: log2(opacity) = -inf => alpha 0 => exact no-op
     if (slot < len) {
       const float4* src = rec + 3 * (size_t)pl[slot];
       p0 = src[0]; p1 = src[1]; p2 = src[2];
@@ -365,8 +367,8 @@ composite_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
             /* --fmad=false); the reference sum is UNFUSED, so the add is done with scalar FADDs */ \
             const float2 m0 = __fmul2_rn(u0, dx), m1 = __fmul2_rn(u1, dy);                       \
             const float2 pw = f2(__fadd_rn(m0.x, m1.x), __fadd_rn(m0.y, m1.y));                  \
-            const float2 e = __fmul2_rn(pw, kLog2e);                                             \
-            const float2 al = __fmul2_rn(f2(ex2_approx(e.x), ex2_approx(e.y)), op);              \
+            const float2 e = __ffma2_rn(pw, kLog2e, op); /* op = (log2(op), log2(op)) */          \
+            const float2 al = f2(ex2_approx(e.x), ex2_approx(e.y));                              \
             float2 ta = __fmul2_rn(T, al);                                                       \
             T = __ffma2_rn(ta, kNeg1, T);                                                        \
             LA = LA && (T.x >= minw);                                                            \
@@ -462,7 +464,7 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
   } else {
     const float op2 = 1.0f / (1.0f + expf(-op));  // the CPU path applies a second sigmoid (:164)
     rec[3 * i + 0] = make_float4(mx, my, -0.5f * i00, -0.5f * i01);
-    rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, op2, colors[3 * i]);
+    rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, log2f(op2), colors[3 * i]);  // log2: see composite_fast_kernel
     op_used = op2;
     int imn = (int)fminf(fmaxf(mnx, -big), big), imx = (int)fminf(fmaxf(mxx, -big), big);
     tx0 = max(floor_div_i(imn - 1, T), 0); tx1 = min(floor_div_i(imx, T), geom.tiles_x - 1);

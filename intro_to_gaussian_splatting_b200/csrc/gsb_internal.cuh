@@ -5,7 +5,7 @@
 //                        x y z | sx sy sz | qw qx qy qz | r g b | opacity_logit      (56 B/Gaussian)
 //   per frame (project): depth_key u32[N]  float_as_uint(z_view), 0xFFFFFFFF when culled
 //                        rec float4[3N]    AoS compositing record, 48 B/Gaussian:
-//                                          {mx,my,a,b} {c,d,op2,r} {g,b,radius,sig_op}
+//                                          {mx,my,a,b} {c,d,log2(op2),r} {g,b,radius,sig_op}
 //                                          a,b,c,d = -0.5 * inverse covariance (exact scaling)
 //                        rect ushort4[N]   tile rect tx0,tx1,ty0,ty1 (count==0 => unused)
 //                        count u32[N]      tiles touched

@@ -252,7 +252,8 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       const float op2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sig1)));
       // conic pre-scaled by -0.5: exact (power of two), so (-0.5*d) @ inv rounds identically (composite.cu)
       rec[3 * i + 0] = make_float4(px, py, -0.5f * i00, -0.5f * i01);
-      rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, op2, cr);
+      // the blend loop evaluates alpha = op2 * exp(power) as exp2(power*log2e + log2(op2)): one FFMA + MUFU.EX2
+      rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, log2f(op2), cr);
       rec[3 * i + 2] = make_float4(cg, cb, rad, sig1);
       rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
       dkey = __float_as_uint(vz);
