@@ -443,16 +443,16 @@ def run_ours(args):
                                     "steps_executed": int(fr.steps)}
             comp_ms = stage_ms_first.get("composite", 0.0)  # views[0] is orbit view 0 on rank 0
             if comp_ms > 0 and clocks and clocks.get("sm_mhz"):
-                # issue-slot roofline of compositing.  0.614 warp-instructions per executed (pixel, Gaussian) step
+                # issue-slot roofline of compositing.  0.580 warp-instructions per executed (pixel, Gaussian) step
                 # is the ncu count for this kernel on this view (smsp__inst_executed.sum / oracle step count,
                 # profiles/r1_summary.md); the peak is 4 schedulers x 148 SMs x the SM clock sampled during the run.
-                warp_inst = 0.614 * fr.steps
+                warp_inst = 0.580 * fr.steps
                 peak = 148 * 4 * clocks["sm_mhz"] * 1e6
                 roofline["issue"] = {"kernel": "composite_fast_kernel", "steps_view0": int(fr.steps),
                                      "composite_ms_view0": comp_ms,
                                      "warp_inst_per_s": warp_inst / (comp_ms * 1e-3),
                                      "peak_warp_inst_per_s": peak, "frac": warp_inst / (comp_ms * 1e-3) / peak,
-                                     "note": "warp instructions = 0.614 x executed pixel-steps (ncu-calibrated)"}
+                                     "note": "warp instructions = 0.580 x executed pixel-steps (ncu-calibrated, profiles/r1_summary.md)"}
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
