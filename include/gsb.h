@@ -130,8 +130,9 @@ int gsb_upload(GsbContext* ctx, int64_t n, const float* xyz, const float* scales
 /* The forward render: projection -> tile binning -> radix sort -> tile ranges -> compositing.
  * Replaces GaussianScene.preprocess + ext.render_image (splat/gaussian_scene.py:263-285).
  * out_image: (H,W,3) fp32, image[y][x][c] like render.cu:83-85; dev-or-host.  `cam`/`params`
- * are host structs, copied before return.  Synchronises the stream once internally to size
- * the key buffers (the tile-instance count K is data dependent). */
+ * are host structs, copied before return.  The call returns once the data-dependent tile-instance
+ * count K has reached the host (mailbox in mapped pinned memory; the stream is NOT drained) and the
+ * rest of the frame is queued. */
 int gsb_render(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, float* out_image,
                void* stream);
 
