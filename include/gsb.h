@@ -88,13 +88,13 @@ typedef struct GsbParams {
                               gsb_join_host_copies(ctx, stream) + a synchronisation of that stream */
 } GsbParams;
 
-/* Stage indices for gsb_stage_times */
+/* Stage indices for gsb_stage_times (CUDA events on the caller's stream) */
 #define GSB_STAGE_PROJECT 0
-#define GSB_STAGE_DEPTH_SORT 1 /* split mode only */
-#define GSB_STAGE_SCAN 2
-#define GSB_STAGE_EMIT 3
-#define GSB_STAGE_SORT 4
-#define GSB_STAGE_RANGES 5
+#define GSB_STAGE_DEPTH_SORT 1 /* per-Gaussian depth sort (SPLIT / BINNED) */
+#define GSB_STAGE_SCAN 2       /* prefix sum of the tile counts */
+#define GSB_STAGE_EMIT 3       /* key emission (includes the wait for the M/K mailbox, normally zero) */
+#define GSB_STAGE_SORT 4       /* radix passes over the K keys (BINNED: per-tile sort) */
+#define GSB_STAGE_RANGES 5     /* tile statistics; runs on the auxiliary stream in FULL/SPLIT and reads 0 there */
 #define GSB_STAGE_COMPOSITE 6
 #define GSB_NUM_STAGES 7
 

@@ -1,38 +1,19 @@
-// binning.cu -- tile binning: single-pass prefix sum of tile counts, key emission, tile ranges.
+// binning.cu -- tile binning: tile statistics (ranges, histograms, K), prefix sum of tile counts, key emission.
 //
 // Replaces the per-tile boolean masks of GaussianScene.render_image
 // (splat/gaussian_scene.py:208-226): instead of an O(tiles*M) mask sweep, every in-view Gaussian is
 // expanded into one (key, payload) pair per tile of its rect,
 //     key = tile_id << 32 | float_as_uint(z_view),  tile_id = ty*tiles_x + tx,  payload = Gaussian index
-//  and the sorted key array is cut into per-tile [start,end) ranges.
+// (SURVEY.md Appendix A.8).  The per-tile [start,end) ranges of the sorted array are known before any key exists:
+// tile_stats_kernel derives them from the 2-D difference grid of tile rects written by the projection kernel.
 //
-// Roofline: HBM.  scan: 4 B read + 4 B written per Gaussian.  emit: 12 B written per key
-// (+ 24 B per Gaussian read).  ranges: 8 B read per key + 8 B per tile.
+// Roofline: HBM.  scan: 8 B read + 4 B written per Gaussian.  emit: 8-12 B written per key (+ 24 B per Gaussian
+// read).  tile stats: 4 B per grid cell read, 8 B per tile written.
 #include "gsb_internal.cuh"
 
 namespace gsb {
 
 namespace {
-
-constexpr uint32_t kFlagShift = 30;
-constexpr uint32_t kFlagAggregate = 1u << kFlagShift;
-constexpr uint32_t kFlagPrefix = 2u << kFlagShift;
-constexpr uint32_t kValueMask = (1u << kFlagShift) - 1u;
-
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 __device__ __forceinline__ uint64_t ld_relaxed64(const uint64_t* p) {
   uint64_t v;
@@ -254,31 +235,6 @@ int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload,
                         uint64_t* keys, cudaStream_t st) {
   if (tiles <= 0) return 0;
   rebuild_keys_kernel<<<(unsigned)((tiles * 32 + 255) / 256), 256, 0, st>>>(ranges, tiles, payload, depth_key, keys);
-  return (int)cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// tile ranges: boundaries of the tile field in the sorted key array.  ranges must be zeroed
-// (empty tiles stay (0,0)).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ranges_kernel(const uint64_t* __restrict__ sorted_keys, int64_t k, uint2* __restrict__ ranges) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= k) return;
-  const uint32_t t = (uint32_t)(sorted_keys[i] >> 32);
-  const uint32_t tp = i > 0 ? (uint32_t)(sorted_keys[i - 1] >> 32) : 0xFFFFFFFFu;
-  if (i == 0 || tp != t) {
-    ranges[t].x = (uint32_t)i;
-    if (i > 0) ranges[tp].y = (uint32_t)i;
-  }
-  if (i == k - 1) ranges[t].y = (uint32_t)k;
-}
-
-int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k, uint2* ranges, cudaStream_t st) {
-  (void)total;
-  if (k == 0) return 0;
-  unsigned blocks = (unsigned)((k + 255) / 256);
-  ranges_kernel<<<blocks, 256, 0, st>>>(sorted_keys, k, ranges);
   return (int)cudaGetLastError();
 }
 

@@ -118,8 +118,6 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
                 KeyT* keys_b, uint32_t* vals_b, const uint32_t* hist, uint32_t* control, bool* result_in_a,
                 int* launches, cudaStream_t st);
 
-int launch_ranges(const uint64_t* sorted_keys, const uint32_t* total, int64_t k, uint2* ranges, cudaStream_t st);
-
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
                      FrameGeom geom, const GsbParams& prm, cudaStream_t st);
 

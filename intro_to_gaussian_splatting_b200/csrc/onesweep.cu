@@ -130,8 +130,7 @@ struct SortSmem {
     KeyT keys[kThreads * kItems];
     uint32_t vals[kThreads * kItems];
   } exch;
-  uint32_t cnt[kWarps][kRadix];
-  uint32_t tile_start[kRadix];
+  alignas(16) uint32_t cnt[kWarps][kRadix];
   uint32_t gofs[kRadix];
   uint32_t scan[2][kWarps];
   uint32_t tile;
@@ -149,7 +148,6 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   constexpr int kTileKeys = kThreads * kItems;
   auto& exch = sm.exch;
   auto& s_cnt = sm.cnt;
-  auto& s_tile_start = sm.tile_start;
   auto& s_gofs = sm.gofs;
   auto& s_scan = sm.scan;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,15 +222,16 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
       if (w < warp) { wa += s_scan[0][w]; wb += s_scan[1][w]; }
     tile_start = wa + a - a_in;
     bin_base = wb + b - b_in;
-    s_tile_start[d] = tile_start;
+    // fold the digit's start inside the tile into the per-warp offsets: one shared load per key in 5a
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s_cnt[w][d] += tile_start;
   }
   __syncthreads();
 
   // 5a. keys -> smem in locally sorted order (gives earlier tiles time to publish before the look-back)
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
-    const uint32_t d = digit_fast(key[i], shift, mask);
-    pos[i] += s_tile_start[d] + s_cnt[warp][d];
+    pos[i] += s_cnt[warp][digit_fast(key[i], shift, mask)];
     exch.keys[pos[i]] = key[i];
   }
 
@@ -324,7 +323,10 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   __shared__ SortSmem<KeyT, kItems> sm;
   const int tid = threadIdx.x;
   if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kWarps * kRadix; i += kThreads) (&sm.cnt[0][0])[i] = 0;
+  {
+    uint4* z = reinterpret_cast<uint4*>(&sm.cnt[0][0]);
+    for (int i = tid; i < kWarps * kRadix / 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
   const uint32_t tile = sm.tile;
   const int valid = (int)min((int64_t)kTileKeys, n - (int64_t)tile * kTileKeys);
