@@ -8,7 +8,8 @@ libgsb_b200.so (csrc/, C ABI in include/gsb.h), hand-written CUDA for sm_100a.
 from .gaussian_scene import GaussianScene  # noqa: F401
 from .gaussians import Gaussians  # noqa: F401
 from .image import GaussianImage  # noqa: F401
-from .rasterizer import Rasterizer  # noqa: F401
+from .rasterizer import Rasterizer, ViewRenderer  # noqa: F401
 from .schema import BasicPointCloud, PreprocessedScene  # noqa: F401
 
-__all__ = ["GaussianScene", "Gaussians", "GaussianImage", "Rasterizer", "PreprocessedScene", "BasicPointCloud"]
+__all__ = ["GaussianScene", "Gaussians", "GaussianImage", "Rasterizer", "ViewRenderer", "PreprocessedScene",
+           "BasicPointCloud"]

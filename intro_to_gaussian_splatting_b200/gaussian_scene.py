@@ -24,7 +24,7 @@ from torch import nn
 from . import _lib
 from .gaussians import Gaussians
 from .image import GaussianImage
-from .rasterizer import Rasterizer
+from .rasterizer import Rasterizer, ViewRenderer
 from .schema import PreprocessedScene
 from .utils import read_camera_file, read_image_file
 
@@ -112,6 +112,23 @@ class GaussianScene(nn.Module):
         rast = self._sync_gaussians()
         img = rast.render(self.images[image_idx].pack(), self._params(tile_size), layout="whc")
         return img.cpu()
+
+    def render_views(self, image_idxs, tile_size: int = 16, out: Optional[torch.Tensor] = None,
+                     frames_in_flight: int = 3) -> torch.Tensor:
+        """Many views at once -> (V,H,W,3).  Not in the reference (it renders one image per call); this is the
+        throughput entry for orbit-style workloads: several frames in flight on independent contexts/streams,
+        optional asynchronous egress into a pinned CPU `out`.  Frames equal render_image_cuda(idx) bit for bit."""
+        g = self.gaussians
+        ts = (g.points, g.scales, g.quaternions, g.colors, g.opacity)
+        sig = tuple((id(t), t._version) for t in ts) + (frames_in_flight,)
+        if getattr(self, "_view_renderer_sig", None) != sig:
+            if getattr(self, "_view_renderer", None) is not None:
+                self._view_renderer.close()
+            self._view_renderer = ViewRenderer(*ts, frames_in_flight=frames_in_flight)
+            self._view_renderer_sig = sig
+            self._view_renderer_refs = ts  # keep the tensors alive so that id() cannot be recycled
+        cams = [self.images[i].pack() for i in image_idxs]
+        return self._view_renderer.render(cams, self._params(tile_size), out=out)
 
     def compile_cuda_ext(self) -> _ExtShim:
         return _ExtShim(self.rasterizer)

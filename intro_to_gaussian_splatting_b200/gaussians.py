@@ -15,14 +15,18 @@ class Gaussians(nn.Module):
     quaternions (N,4) wxyz, default identity; opacity (N,1) logit, default logit(0.9999)
     (splat/gaussians.py:19-33).  Overwrite the attributes to load a trained / synthetic set.
 
-    The reference ctor also writes `<model_path>/point_cloud.ply` through a Python tuple loop
-    (splat/gaussians.py:17-18, splat/utils.py:102-125); nothing reads it back, it needs `plyfile`,
-    and it is outside the render path, so it is not reproduced (out of scope)."""
+    The reference ctor also writes `<model_path>/point_cloud.ply` through plyfile and a Python tuple loop
+    (splat/gaussians.py:17-18, splat/utils.py:102-125); nothing on the render path reads it back, so here it is
+    opt-in (`write_ply=True`, ply_io.storePly: same vertex layout, one numpy structured array)."""
 
-    def __init__(self, points: torch.Tensor, colors: torch.Tensor, model_path: str = ".") -> None:
+    def __init__(self, points: torch.Tensor, colors: torch.Tensor, model_path: str = ".", write_ply: bool = False) -> None:
         super().__init__()
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.point_cloud_path = os.path.join(model_path, "point_cloud.ply")
+        if write_ply:  # the reference always does this (splat/gaussians.py:17-18); here it is opt-in and fast
+            from .ply_io import storePly
+
+            storePly(self.point_cloud_path, points.detach().cpu().numpy(), colors.detach().cpu().numpy())
         self.points = points.clone().requires_grad_(True).to(self.device).float()
         self.colors = (colors / 256).clone().requires_grad_(True).to(self.device).float()
         self.scales = torch.ones((len(self.points), 3)).to(self.device).float() * 0.001

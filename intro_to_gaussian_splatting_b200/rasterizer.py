@@ -8,7 +8,7 @@ fallback path of any kind.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -188,3 +188,56 @@ class Rasterizer:
                                                int(begin_bit), int(end_bit), self._stream()), "gsb_sort_pairs_u64")
             torch.cuda.current_stream(self.device).synchronize()
         return kout, vout
+
+
+class ViewRenderer:
+    """Throughput rendering of many views of one Gaussian set: `frames_in_flight` independent contexts, each on
+    its own CUDA stream, take the views round-robin, so the latency-bound front of one frame (projection, depth
+    sort, binning) overlaps the issue-bound compositing of another.  This is how the view-sharded orbit workload is
+    driven on every rank (bench.py); the frames are bit-identical to frames rendered one at a time."""
+
+    def __init__(self, points, scales, quaternions, colors, opacity, frames_in_flight: int = 3,
+                 device: Optional[int] = None) -> None:
+        self.rasts = [Rasterizer(device) for _ in range(max(1, int(frames_in_flight)))]
+        self.device = self.rasts[0].device
+        for r in self.rasts:
+            r.upload(points, scales, quaternions, colors, opacity)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.rasts]
+
+    def close(self) -> None:
+        for r in self.rasts:
+            r.close()
+
+    def render(self, cams: Sequence[GsbCamera], params: Optional[GsbParams] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """cams: V packed cameras of one image size.  out: (V,H,W,3) fp32, CUDA or pinned CPU (asynchronous egress);
+        allocated on the device when omitted.  Work is ordered after the current stream on entry, and the current
+        stream is ordered after all of it on return (synchronise it before reading a CPU `out`)."""
+        if len(cams) == 0:
+            raise RuntimeError("ViewRenderer.render: no cameras")
+        H, W = cams[0].height, cams[0].width
+        if out is None:
+            out = torch.empty((len(cams), H, W, 3), dtype=torch.float32, device=self.device)
+        if tuple(out.shape) != (len(cams), H, W, 3) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("ViewRenderer.render: out must be a contiguous float32 (V,H,W,3) tensor")
+        params = params or _lib.default_params()
+        if not out.is_cuda:
+            params = _lib.default_params(**{f: getattr(params, f) for f, _ in GsbParams._fields_})
+            params.async_host_copy = 1
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in self.streams:
+            st.wait_event(fork)
+        for i, cam in enumerate(cams):
+            f = i % len(self.rasts)
+            with torch.cuda.stream(self.streams[f]):
+                self.rasts[f].render(cam, params, out=out[i])
+        for f, st in enumerate(self.streams):
+            with torch.cuda.stream(st):
+                if not out.is_cuda:
+                    self.rasts[f].join_host_copies()
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
+        return out

@@ -15,6 +15,7 @@ import math
 import torch
 
 from .colmap_io import read_camera_file, read_image_file  # noqa: F401  (same import surface as splat.utils)
+from .ply_io import fetchPly, storePly  # noqa: F401
 
 
 def inverse_sigmoid(x: torch.Tensor) -> torch.Tensor:

@@ -148,3 +148,18 @@ def test_three_contexts_in_flight_match_serial_frames():
     finally:
         for r in rasts:
             r.close()
+
+
+def test_render_views_equals_single_frames():
+    sc, _, d = scene_and_images("small", n_views=5)
+    g = Gaussians(points=sc.xyz.clone(), colors=sc.rgb255.clone(), model_path=d)
+    g.scales, g.quaternions, g.opacity = sc.scales.cuda(), sc.quats.cuda(), sc.opacity_logit.cuda()
+    scene = GaussianScene(colmap_path=d, gaussians=g)
+    single = torch.stack([scene.render_image_cuda(i) for i in (1, 2, 3, 4, 5)])
+    many = scene.render_views([1, 2, 3, 4, 5])
+    torch.cuda.synchronize()
+    assert torch.equal(many, single)
+    host = torch.empty((5, 96, 160, 3), dtype=torch.float32).pin_memory()
+    scene.render_views([5, 4, 3, 2, 1], out=host)
+    torch.cuda.synchronize()
+    assert torch.equal(host, single.flip(0).cpu())

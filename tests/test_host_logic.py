@@ -1,0 +1,78 @@
+"""Host-side logic that needs no GPU: COLMAP readers (text + binary), PLY round trip, synthetic scenes."""
+
+import os
+import struct
+import tempfile
+
+import numpy as np
+import torch
+
+from intro_to_gaussian_splatting_b200 import Gaussians
+from intro_to_gaussian_splatting_b200.colmap_io import (read_camera_file, read_cameras_binary, read_image_file,
+                                                        read_images_binary)
+from intro_to_gaussian_splatting_b200.ply_io import fetchPly, storePly
+from intro_to_gaussian_splatting_b200.synth import make_scene, write_colmap_text
+
+
+def test_colmap_text_and_binary_agree():
+    sc = make_scene("small", n_views=3)
+    d = tempfile.mkdtemp()
+    write_colmap_text(sc, d)
+    cams, imgs = read_camera_file(d), read_image_file(d)
+    assert list(cams) == [1] and cams[1].model == "PINHOLE" and (cams[1].width, cams[1].height) == (160, 96)
+    assert sorted(imgs) == [1, 2, 3] and imgs[2].name == "v1.jpg" and imgs[2].camera_id == 1
+    # the same model in COLMAP's binary layout (written here by hand) must parse to the same values,
+    # and the *.bin files win over *.txt like in splat/utils.py:269-290
+    with open(os.path.join(d, "cameras.bin"), "wb") as f:
+        f.write(struct.pack("<Q", 1))
+        f.write(struct.pack("<iiQQ", 1, 1, 160, 96))
+        f.write(struct.pack("<dddd", *cams[1].params))
+    with open(os.path.join(d, "images.bin"), "wb") as f:
+        f.write(struct.pack("<Q", len(imgs)))
+        for i in sorted(imgs):
+            im = imgs[i]
+            f.write(struct.pack("<idddddddi", i, *im.qvec, *im.tvec, im.camera_id))
+            f.write(im.name.encode() + b"\x00")
+            f.write(struct.pack("<Q", 2))
+            f.write(struct.pack("<ddq", 1.0, 2.0, 7) + struct.pack("<ddq", 3.0, 4.0, -1))
+    cb, ib = read_cameras_binary(os.path.join(d, "cameras.bin")), read_images_binary(os.path.join(d, "images.bin"))
+    assert np.array_equal(cb[1].params, cams[1].params) and cb[1].model == "PINHOLE"
+    for i in imgs:
+        assert np.array_equal(ib[i].qvec, imgs[i].qvec) and np.array_equal(ib[i].tvec, imgs[i].tvec)
+        assert ib[i].name == imgs[i].name
+    assert read_camera_file(d)[1].width == 160 and read_image_file(d)[3].name == "v2.jpg"
+    try:
+        read_camera_file(tempfile.mkdtemp())
+        assert False, "missing model must raise like the reference (ValueError)"
+    except ValueError:
+        pass
+
+
+def test_ply_round_trip_and_constructor_side_effect():
+    sc = make_scene("tiny")
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "pc.ply")
+    storePly(path, sc.xyz.numpy(), sc.rgb255.numpy())
+    pc = fetchPly(path)
+    assert np.array_equal(pc.points, sc.xyz.numpy())
+    assert np.array_equal(np.rint(pc.colors * 255).astype(np.uint8), sc.rgb255.numpy().astype(np.uint8))
+    assert pc.normals.shape == (300, 3) and not pc.normals.any()
+    g = Gaussians(sc.xyz, sc.rgb255, model_path=d, write_ply=True)
+    assert os.path.exists(g.point_cloud_path) and fetchPly(g.point_cloud_path).points.shape == (300, 3)
+    # container defaults of the reference (splat/gaussians.py:20-33)
+    assert torch.allclose(g.colors.cpu(), sc.rgb255 / 256) and float(g.scales[0, 0]) == float(np.float32(0.001))
+    assert torch.equal(g.quaternions.cpu()[0], torch.tensor([1.0, 0, 0, 0]))
+    assert abs(float(g.opacity[0]) - float(np.log(0.9999 / (1 - 0.9999)))) < 1e-2
+    c3 = g.get_3d_covariance_matrix()
+    assert c3.shape == (300, 3, 3) and torch.allclose(c3[0].cpu(), torch.eye(3) * 1e-6, atol=1e-9)
+
+
+def test_synth_is_deterministic_and_matches_its_spec():
+    a, b = make_scene("small"), make_scene("small")
+    for k in ("xyz", "rgb255", "scales", "quats", "opacity_logit"):
+        assert torch.equal(getattr(a, k), getattr(b, k))
+    assert a.xyz.abs().max() <= 3.0 and 0 <= a.rgb255.min() and a.rgb255.max() < 255
+    assert a.scales.min() >= np.exp(-6.0) * 0.999 and a.scales.max() <= np.exp(-3.0) * 1.001
+    c1 = make_scene("cfg1", n_override=10)
+    assert torch.all(c1.scales == 0.01) and torch.all(c1.quats[:, 0] == 1) and len(c1.views) == 1
+    assert len(make_scene("cfg4", n_override=4).views) == 256
