@@ -396,6 +396,7 @@ composite_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
   }
 }
 
+
 }  // namespace
 
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,

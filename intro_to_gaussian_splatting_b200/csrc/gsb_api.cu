@@ -12,6 +12,7 @@
 // Both leave bit-identical sorted (key, payload) arrays: an LSD radix sort orders by the low (depth)
 // digits first, and every tile instance of a Gaussian shares those digits, so they can be sorted once
 // per Gaussian BEFORE the expansion instead of once per instance after it.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -173,11 +174,14 @@ int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t 
     return GSB_OK;
   }
   volatile uint32_t* box = c->pinned;
+  const auto t0 = std::chrono::steady_clock::now();
   for (uint64_t spins = 0; box[4] != c->seq; ++spins) {
     if ((spins & 0x3FFF) == 0x3FFF) {
       cudaError_t q = cudaStreamQuery(c->aux);
       if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
       if (q == cudaSuccess && box[4] != c->seq) return GSB_E_INTERNAL;  // kernel finished, mailbox never written
+      // a stream that never runs (e.g. waiting on an event nobody records) must not hang the caller for ever
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) return GSB_E_INTERNAL;
     }
   }
   *m = box[0];
@@ -386,7 +390,7 @@ const char* gsb_error_string(int s) {
     case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; fewer than 2^32-1 tile instances)";
     case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case GSB_E_ALLOC: return "device memory allocation failed";
-    case GSB_E_INTERNAL: return "internal consistency check failed (scan total != tile-grid total)";
+    case GSB_E_INTERNAL: return "internal error (device-side consistency check failed, or the stream made no progress)";
     default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown error";
   }
 }
