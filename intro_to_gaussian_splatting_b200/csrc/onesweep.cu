@@ -118,6 +118,22 @@ __device__ __forceinline__ uint32_t digit64(uint64_t k, int shift, uint32_t mask
   const uint32_t v = shift >= 32 ? (hi >> (shift - 32)) : __funnelshift_r(lo, hi, shift);  // warp-uniform branch
   return v & mask;
 }
+// Lanes holding the same digit, from one ballot per digit bit.  `__match_any_sync` compiles to MATCH.ANY, which
+// costs ~30 cycles of a per-SM unit per warp instruction here (clock64 instrumentation: 11 000 of a tile's 23 600
+// cycles went into 16 matches per thread); a ballot costs ~4, so digits narrower than 8 bits get cheaper.
+__device__ __forceinline__ unsigned match_digit(uint32_t d, int bits) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < kRadixBits; ++b) {
+    if (b < bits) {  // warp-uniform
+      const bool bit = (d >> b) & 1u;
+      const unsigned m = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? m : ~m;
+    }
+  }
+  return peers;
+}
+
 template <typename KeyT>
 __device__ __forceinline__ uint32_t digit_fast(KeyT k, int shift, uint32_t mask) {
   if constexpr (sizeof(KeyT) == 8) return digit64((uint64_t)k, shift, mask);
@@ -140,9 +156,9 @@ struct SortSmem {
 template <typename KeyT, int kItems, int kMode, bool kFull, typename W>
 __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const KeyT* __restrict__ keys_in,
                                               const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                                              uint32_t* __restrict__ vals_out, int64_t n, int shift, uint32_t mask,
-                                              const uint32_t* __restrict__ hist, W* status, uint32_t tile,
-                                              int valid) {
+                                              uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+                                              uint32_t mask, const uint32_t* __restrict__ hist, W* status,
+                                              uint32_t tile, int valid) {
   using SW = StatusWord<W>;
   constexpr W kWAgg = (W)1 << SW::kShift, kWPre = (W)2 << SW::kShift, kWMask = ((W)1 << SW::kShift) - 1;
   constexpr int kTileKeys = kThreads * kItems;
@@ -169,19 +185,25 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     }
   }
 
-  // 3. stable ranks inside the warp, written for instruction-level parallelism: all matches first, then all
-  //    shared-memory atomics (leaders only; an ATOMS returns the running count, and shared atomics of one
-  //    warp retire in issue order, which is what keeps equal digits in item order), then all broadcasts.
+  // 3. stable ranks inside the warp: all ballot matches first (independent), then the running counts (leaders
+  //    only, in item order), then all broadcasts.
   unsigned peers[kItems];
   uint32_t pos[kItems];
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) peers[i] = __match_any_sync(0xffffffffu, digit_fast(key[i], shift, mask));
+  for (int i = 0; i < kItems; ++i) peers[i] = match_digit(digit_fast(key[i], shift, mask), bits);
+  // Running per-digit count of this warp: a plain load + store by the group leader.  Warp instructions reach
+  // shared memory in program order, so item i+1 sees item i's update; `volatile` keeps the compiler from
+  // reordering the accesses.
+  volatile uint32_t* wcnt = s_cnt[warp];
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     pos[i] = 0;
-    if ((peers[i] & lt_mask) == 0u)  // lowest lane of its peer group == the leader
-      pos[i] = atomicAdd(&s_cnt[warp][digit_fast(key[i], shift, mask)], (uint32_t)__popc(peers[i]));
+    if ((peers[i] & lt_mask) == 0u) {  // lowest lane of its peer group == the leader
+      const uint32_t d = digit_fast(key[i], shift, mask);
+      pos[i] = wcnt[d];
+      wcnt[d] = pos[i] + (uint32_t)__popc(peers[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < kItems; ++i)
@@ -238,7 +260,8 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   // 4b. decoupled look-back for this thread's digit.  Predecessor words are fetched in BATCHES of
   //     independent loads (2 first -- in steady state the nearest tiles already hold an inclusive prefix --
   //     then 8 at a time): at the start of a pass several hundred tiles are in flight with only their
-  //     aggregates published, and a one-at-a-time walk pays one L2 round trip for each of them.
+  //     aggregates published, and a one-at-a-time walk pays one L2 round trip for each of them.  (Rounds of 32
+  //     were measured slower: most of this phase is spent WAITING for a slow predecessor's aggregate, not walking.)
   {
     uint32_t excl = 0;
     if (tile != 0) {
@@ -313,8 +336,11 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   }
 }
 
+#ifndef GSB_SORT_MINBLOCKS16
+#define GSB_SORT_MINBLOCKS16 3
+#endif
 template <typename KeyT, int kItems, int kMode, typename W>
-__global__ void __launch_bounds__(kThreads, kItems == 8 ? 4 : 3)
+__global__ void __launch_bounds__(kThreads, kItems == 8 ? 4 : GSB_SORT_MINBLOCKS16)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                 const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
@@ -332,9 +358,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   const int valid = (int)min((int64_t)kTileKeys, n - (int64_t)tile * kTileKeys);
   const uint32_t mask = (1u << bits) - 1u;
   if (valid == kTileKeys)
-    onesweep_tile<KeyT, kItems, kMode, true, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
+    onesweep_tile<KeyT, kItems, kMode, true, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, bits, mask, hist, status, tile, valid);
   else
-    onesweep_tile<KeyT, kItems, kMode, false, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, status, tile, valid);
+    onesweep_tile<KeyT, kItems, kMode, false, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, bits, mask, hist, status, tile, valid);
 }
 
 }  // namespace
