@@ -45,6 +45,8 @@ extern "C" {
 #define GSB_E_NO_DEVICE (-5)     /* no usable CUDA device: the library has NO CPU fallback */
 #define GSB_E_ALLOC (-6)
 #define GSB_E_INTERNAL (-7)   /* a device-side consistency check failed */
+#define GSB_E_NO_SAVED (-8)   /* gsb_render_backward: the last render of this context did not save_for_backward,
+                                 or camera / params / scene changed since */
 
 /* ---- compositing semantics ---- */
 #define GSB_SEM_REF_CPU 0 /* splat/gaussian_scene.py:146-238: the parity target */
@@ -86,6 +88,8 @@ typedef struct GsbParams {
   int32_t async_host_copy; /* 1: when the output pointer is HOST memory, copy the image on the context's copy
                               stream so that it overlaps the next frame; the host buffer is valid only after
                               gsb_join_host_copies(ctx, stream) + a synchronisation of that stream */
+  int32_t save_for_backward; /* 1: gsb_render also keeps, per pixel, the number of blended Gaussians and the final
+                                transmittance, so that gsb_render_backward can follow (REF_CPU semantics only) */
 } GsbParams;
 
 /* Stage indices for gsb_stage_times (CUDA events on the caller's stream) */
@@ -140,6 +144,18 @@ int gsb_render(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, f
  * GsbParams.async_host_copy).  After this call, work queued on `stream` -- or a synchronisation of it -- is
  * ordered after those copies. */
 int gsb_join_host_copies(GsbContext* ctx, void* stream);
+
+/* Backward pass of the LAST gsb_render of this context (the reference announces training,
+ * README.md:3, and marks splat/gaussians.py:19-21 requires_grad, but never wrote it).  That render must have been
+ * made with params.save_for_backward = 1 and the same camera / params (compared bytewise; GSB_E_NO_SAVED otherwise).
+ * grad_image: dL/d image, (H,W,3) fp32, device or host.  Outputs (device or host, any may be NULL), in the
+ * reference's attribute layouts: grad_points (N,3), grad_scales (N,3), grad_quats (N,4), grad_colors (N,3),
+ * grad_opacity (N,1) -- the gradient wrt the opacity LOGIT.  Tile membership, depth order, early termination and
+ * the clamps are treated as piecewise constant.  Sums use float atomics: results are reproducible to rounding,
+ * not bit for bit. */
+int gsb_render_backward(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, const float* grad_image,
+                        float* grad_points, float* grad_scales, float* grad_quats, float* grad_colors,
+                        float* grad_opacity, void* stream);
 
 /* Same frame, egress variants: (W,H,3) layout of the reference CPU
  * path (image[x][y][c], splat/gaussian_scene.py:206,:227), or 8-bit (H,W,3) clamp(v,0,1)*255. */

@@ -5,6 +5,7 @@ Host side: this package (same names as the reference's `splat` package).  Device
 libgsb_b200.so (csrc/, C ABI in include/gsb.h), hand-written CUDA for sm_100a.
 """
 
+from .autograd import render_differentiable  # noqa: F401
 from .gaussian_scene import GaussianScene  # noqa: F401
 from .gaussians import Gaussians  # noqa: F401
 from .image import GaussianImage  # noqa: F401
@@ -12,4 +13,4 @@ from .rasterizer import Rasterizer, ViewRenderer  # noqa: F401
 from .schema import BasicPointCloud, PreprocessedScene  # noqa: F401
 
 __all__ = ["GaussianScene", "Gaussians", "GaussianImage", "Rasterizer", "ViewRenderer", "PreprocessedScene",
-           "BasicPointCloud"]
+           "BasicPointCloud", "render_differentiable"]

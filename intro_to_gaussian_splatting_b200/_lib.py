@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "gsb_version", "gsb_error_string", "gsb_default_params", "gsb_create", "gsb_destroy", "gsb_upload",
     "gsb_render", "gsb_render_wh", "gsb_render_u8", "gsb_preprocess", "gsb_render_image", "gsb_frame_info",
     "gsb_debug_projection", "gsb_debug_sorted_keys", "gsb_debug_emitted_keys", "gsb_debug_tile_ranges",
-    "gsb_stage_times", "gsb_sort_pairs_u64", "gsb_join_host_copies",
+    "gsb_stage_times", "gsb_sort_pairs_u64", "gsb_join_host_copies", "gsb_render_backward",
 )
 
 
@@ -59,6 +59,7 @@ class GsbParams(C.Structure):
         ("sort_mode", C.c_int32),
         ("collect_stage_times", C.c_int32),
         ("async_host_copy", C.c_int32),
+        ("save_for_backward", C.c_int32),
     ]
 
 
@@ -113,6 +114,7 @@ def load() -> C.CDLL:
     lib.gsb_stage_times.argtypes = [vp, C.POINTER(C.c_float * GSB_NUM_STAGES)]
     lib.gsb_sort_pairs_u64.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, vp]
     lib.gsb_join_host_copies.argtypes = [vp, vp]
+    lib.gsb_render_backward.argtypes = [vp, C.POINTER(GsbCamera), C.POINTER(GsbParams)] + [vp] * 7
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("gsb_error_string", "gsb_default_params", "gsb_destroy"):

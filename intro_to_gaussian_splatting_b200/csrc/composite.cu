@@ -147,6 +147,10 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 constexpr int kFastThreads = 64;
 constexpr int kFastBatch = 128;                        // records per stage
 constexpr int kFastPerThread = kFastBatch / kFastThreads;  // records each thread stages
+#ifndef GSB_FAST_UNROLL
+#define GSB_FAST_UNROLL 4
+#endif
+constexpr int kFastUnroll = GSB_FAST_UNROLL;                 // Gaussians between two warp votes
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -156,10 +160,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// kAux (save_for_backward): also records, per pixel, how many Gaussians were blended (the list prefix [0, n)) and
+// the transmittance after the last of them -- what the back-to-front gradient pass starts from (backward.cu).
+template <bool kAux>
 __global__ void __launch_bounds__(kFastThreads)
 composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
-                      const float4* __restrict__ rec, float* __restrict__ image,
-                      const __grid_constant__ CompositeArgs a) {
+                      const float4* __restrict__ rec, float* __restrict__ image, float* __restrict__ aux_t,
+                      uint32_t* __restrict__ aux_n, const __grid_constant__ CompositeArgs a) {
   __shared__ __align__(16) float4 sm[2][kFastBatch * 3];
 
   const int tile = blockIdx.x;
@@ -180,6 +187,8 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   float T0 = 1.f, T1 = 1.f, T2 = 1.f, T3 = 1.f;
   float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
   float r2 = 0.f, g2 = 0.f, b2 = 0.f, r3 = 0.f, g3 = 0.f, b3 = 0.f;
+  uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;          // kAux only
+  float tf0 = 1.f, tf1 = 1.f, tf2 = 1.f, tf3 = 1.f;  // kAux only
 
   const float4 null0 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 null1 = make_float4(0.f, 0.f, -INFINITY, 0.f);  // log2(opacity) = -inf => alpha = 0 => exact no-op
@@ -221,16 +230,16 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     if (warp_live) {
       const float4* p = sm[buf];
 #pragma unroll 1
-      for (int i = 0; i < kFastBatch; i += 4) {
+      for (int i = 0; i < kFastBatch; i += kFastUnroll) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kFastUnroll; ++u) {
           const float4 q0 = p[0];  // mx, my, a, b
           const float4 q1 = p[1];  // c, d, op, r
           const float2 q2 = *reinterpret_cast<const float2*>(p + 2);  // g, b
           p += 3;
           const float dx = q0.x - fx;
           const float ta_ = __fmul_rn(dx, q0.z), tb_ = __fmul_rn(dx, q0.w);
-#define GSB_PIXEL_STEP(FY, T, LIVE, R, G, B)                                               \
+#define GSB_PIXEL_STEP(FY, T, LIVE, R, G, B, NC, TF)                                       \
           {                                                                                \
             const float dy = q0.y - FY;                                                    \
             const float u0 = __fmaf_rn(dy, q1.x, ta_);                                     \
@@ -241,11 +250,12 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             T = T - ta;                                                                    \
             LIVE = LIVE && (T >= minw);                                                    \
             if (LIVE) { R = fmaf(ta, q1.w, R); G = fmaf(ta, q2.x, G); B = fmaf(ta, q2.y, B); } \
+            if (kAux) { if (LIVE) { NC += 1; TF = T; } }                                   \
           }
-          GSB_PIXEL_STEP(fy0, T0, l0, r0, g0, b0)
-          GSB_PIXEL_STEP(fy1, T1, l1, r1, g1, b1)
-          GSB_PIXEL_STEP(fy2, T2, l2, r2, g2, b2)
-          GSB_PIXEL_STEP(fy3, T3, l3, r3, g3, b3)
+          GSB_PIXEL_STEP(fy0, T0, l0, r0, g0, b0, n0, tf0)
+          GSB_PIXEL_STEP(fy1, T1, l1, r1, g1, b1, n1, tf1)
+          GSB_PIXEL_STEP(fy2, T2, l2, r2, g2, b2, n2, tf2)
+          GSB_PIXEL_STEP(fy3, T3, l3, r3, g3, b3, n3, tf3)
 #undef GSB_PIXEL_STEP
         }
         if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) { warp_live = false; break; }
@@ -261,6 +271,14 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     if (py0 + 1 < a.height) { o[row] = r1; o[row + 1] = g1; o[row + 2] = b1; }
     if (py0 + 2 < a.height) { o[2 * row] = r2; o[2 * row + 1] = g2; o[2 * row + 2] = b2; }
     if (py0 + 3 < a.height) { o[3 * row] = r3; o[3 * row + 1] = g3; o[3 * row + 2] = b3; }
+    if (kAux) {
+      // a null record (tail padding of the last batch) passes the LIVE test with alpha = 0: clamp to the list
+      const size_t p = (size_t)py0 * a.width + px, w = (size_t)a.width;
+      if (py0 < a.height) { aux_t[p] = tf0; aux_n[p] = min(n0, len); }
+      if (py0 + 1 < a.height) { aux_t[p + w] = tf1; aux_n[p + w] = min(n1, len); }
+      if (py0 + 2 < a.height) { aux_t[p + 2 * w] = tf2; aux_n[p + 2 * w] = min(n2, len); }
+      if (py0 + 3 < a.height) { aux_t[p + 3 * w] = tf3; aux_n[p + 3 * w] = min(n3, len); }
+    }
   }
 }
 
@@ -400,7 +418,7 @@ composite_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
 }  // namespace
 
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
-                     FrameGeom geom, const GsbParams& prm, cudaStream_t st) {
+                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, cudaStream_t st) {
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
   CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max};
@@ -408,10 +426,12 @@ int launch_composite(const uint2* ranges, const uint32_t* payload, const float4*
   // for the scalar kernel -- FFMA2/FMUL2/FADD2 halve the issue slots (289 M vs 387 M warp instructions) but
   // occupy the FMA pipe for two cycles each, so the pipe-bound time is unchanged (profiles/r1_summary.md).
   static const int variant = [] { const char* e = std::getenv("GSB_COMPOSITE"); return e ? std::atoi(e) : 1; }();
-  if (variant == 2)
+  if (aux_t && aux_n)
+    composite_fast_kernel<true><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, aux_t, aux_n, a);
+  else if (variant == 2)
     composite_packed_kernel<<<tiles, kPkThreads, 0, st>>>(ranges, payload, rec, image, a);
   else
-    composite_fast_kernel<<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, a);
+    composite_fast_kernel<false><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, nullptr, nullptr, a);
   return (int)cudaGetLastError();
 }
 

@@ -93,6 +93,12 @@ struct GsbContext {
   DevBuf keys_a, keys_b, vals_a, vals_b;
   DevBuf ranges, control, control2;
   DevBuf image, image2, scratch;
+  // save_for_backward: per-pixel blended count / final transmittance of the last frame; gradient scratch
+  DevBuf aux_t, aux_n, grad2d, grad_stage;
+  bool have_saved = false;
+  GsbCamera saved_cam{};
+  GsbParams saved_prm{};
+  uint64_t scene_gen = 0, saved_gen = 0;
   uint32_t* pinned = nullptr;  // mailbox written by tile_stats_kernel: [0]=M, [2..3]=K, [4]=frame sequence number
   uint32_t* pinned_dev = nullptr;  // device alias of the mailbox
   uint32_t seq = 0;
@@ -319,6 +325,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   int launches = 0;
   c->have_frame = false;
   c->have_order = false;
+  c->have_saved = false;
   std::memset(&c->info, 0, sizeof(c->info));
   c->info.n = n; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
   StageTimer tm{c, st, prm->collect_stage_times != 0};
@@ -364,12 +371,29 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   if (!prm->full_cover)  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
     GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
   const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
-  GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, *prm, st));
+  float* aux_t = nullptr;
+  uint32_t* aux_n = nullptr;
+  if (prm->save_for_backward) {
+    const size_t px = (size_t)cam->width * cam->height;
+    GSB_TRY(c->aux_t.ensure(px * 4));
+    GSB_TRY(c->aux_n.ensure(px * 4));
+    aux_t = c->aux_t.as<float>();
+    aux_n = c->aux_n.as<uint32_t>();
+    if (!prm->full_cover) GSB_CUDA_TRY(cudaMemsetAsync(aux_n, 0, px * 4, st));  // pixels outside the grid: nothing blended
+  }
+  GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, *prm,
+                                             aux_t, aux_n, st));
   if (geom.tiles_x * geom.tiles_y > 0) ++launches;
   tm.mark(GSB_STAGE_COMPOSITE);
   c->info.kernel_launches = launches;
   c->frame_rows = n;
   c->have_frame = true;
+  if (prm->save_for_backward) {
+    c->have_saved = true;
+    c->saved_cam = *cam;
+    c->saved_prm = *prm;
+    c->saved_gen = c->scene_gen;
+  }
   finish_times(c, st, tm.on);
   return GSB_OK;
 }
@@ -391,6 +415,7 @@ const char* gsb_error_string(int s) {
     case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case GSB_E_ALLOC: return "device memory allocation failed";
     case GSB_E_INTERNAL: return "internal error (device-side consistency check failed, or the stream made no progress)";
+    case GSB_E_NO_SAVED: return "no saved frame for the backward pass (render with save_for_backward = 1 and the same camera / params first)";
     default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown error";
   }
 }
@@ -410,6 +435,7 @@ void gsb_default_params(GsbParams* p) {
   p->sort_mode = GSB_SORT_AUTO;
   p->collect_stage_times = 0;
   p->async_host_copy = 0;
+  p->save_for_backward = 0;
 }
 
 int gsb_create(GsbContext** out, int device) {
@@ -477,6 +503,8 @@ int gsb_upload(GsbContext* c, int64_t n, const float* xyz, const float* scales, 
   cudaStream_t st = (cudaStream_t)stream;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   c->have_frame = false;
+  c->have_saved = false;
+  ++c->scene_gen;
   c->n = n;
   c->n_pad = (n + 3) & ~(int64_t)3;
   if (n == 0) return GSB_OK;
@@ -538,6 +566,55 @@ int gsb_render(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float*
   GSB_TRY(c->image.ensure(bytes));
   GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
   GSB_CUDA_TRY(cudaMemcpyAsync(out_image, c->image.p, bytes, cudaMemcpyDeviceToHost, st));
+  return GSB_OK;
+}
+
+int gsb_render_backward(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, const float* grad_image,
+                        float* grad_points, float* grad_scales, float* grad_quats, float* grad_colors,
+                        float* grad_opacity, void* stream) {
+  if (!c || !grad_image) return GSB_E_INVALID_ARG;
+  GSB_TRY(check_params(cam, prm));
+  if (!c->have_frame || !c->have_saved || c->saved_gen != c->scene_gen ||
+      std::memcmp(&c->saved_cam, cam, sizeof(GsbCamera)) != 0 || std::memcmp(&c->saved_prm, prm, sizeof(GsbParams)) != 0)
+    return GSB_E_NO_SAVED;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSB_CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t n = c->n;
+  if (n == 0) return GSB_OK;
+  FrameGeom geom{cam->width, cam->height, c->info.tiles_x, c->info.tiles_y};
+  const size_t img_bytes = (size_t)cam->width * cam->height * 3 * sizeof(float);
+  const float* g_img = grad_image;
+  if (!is_device_pointer(grad_image)) {
+    GSB_TRY(c->image2.ensure(img_bytes));
+    GSB_CUDA_TRY(cudaMemcpyAsync(c->image2.p, grad_image, img_bytes, cudaMemcpyHostToDevice, st));
+    g_img = c->image2.as<float>();
+  }
+  GSB_TRY(c->grad2d.ensure((size_t)n * 12 * sizeof(float)));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->grad2d.p, 0, (size_t)n * 12 * sizeof(float), st));
+  const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
+  GSB_CUDA_TRY((cudaError_t)launch_composite_backward(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), g_img,
+                                                      c->aux_t.as<float>(), c->aux_n.as<uint32_t>(),
+                                                      c->grad2d.as<float>(), geom, *prm, st));
+  // outputs: device pointers are written directly; host / NULL ones go through one staging block
+  float* out[5] = {grad_points, grad_scales, grad_quats, grad_colors, grad_opacity};
+  const int width[5] = {3, 3, 4, 3, 1};
+  float* dev[5];
+  size_t need = 0;
+  for (int i = 0; i < 5; ++i)
+    if (!out[i] || !is_device_pointer(out[i])) need += (size_t)n * width[i] * sizeof(float);
+  if (need) GSB_TRY(c->grad_stage.ensure(need));
+  size_t off = 0;
+  for (int i = 0; i < 5; ++i) {
+    if (out[i] && is_device_pointer(out[i])) { dev[i] = out[i]; continue; }
+    dev[i] = reinterpret_cast<float*>(c->grad_stage.as<char>() + off);
+    off += (size_t)n * width[i] * sizeof(float);
+  }
+  GSB_CUDA_TRY((cudaError_t)launch_project_backward(c->planes.as<float>(), n, c->n_pad, *cam, *prm,
+                                                    c->depth_key.as<uint32_t>(), c->count.as<uint32_t>(),
+                                                    c->grad2d.as<float>(), dev[0], dev[1], dev[2], dev[3], dev[4], st));
+  for (int i = 0; i < 5; ++i)
+    if (out[i] && dev[i] != out[i])
+      GSB_CUDA_TRY(cudaMemcpyAsync(out[i], dev[i], (size_t)n * width[i] * sizeof(float), cudaMemcpyDeviceToHost, st));
   return GSB_OK;
 }
 
@@ -705,7 +782,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
     GSB_CUDA_TRY((cudaError_t)launch_composite_cu(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), c->bbox.as<float4>(),
                                                   dev_image, geom, prm, st));
   else
-    GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, prm, st));
+    GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, prm, nullptr, nullptr, st));
   if (geom.tiles_x * geom.tiles_y > 0) ++launches;
   tm.mark(GSB_STAGE_COMPOSITE);
   if (host_out) GSB_CUDA_TRY(cudaMemcpyAsync(out_image, dev_image, bytes, cudaMemcpyDeviceToHost, st));

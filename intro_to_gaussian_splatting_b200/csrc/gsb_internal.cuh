@@ -118,8 +118,22 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
                 KeyT* keys_b, uint32_t* vals_b, const uint32_t* hist, uint32_t* control, bool* result_in_a,
                 int* launches, cudaStream_t st);
 
+// aux_t / aux_n (both or neither; save_for_backward): per pixel, transmittance after the last blended Gaussian
+// and the number of blended Gaussians (the prefix [0, n) of the tile's list)
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
-                     FrameGeom geom, const GsbParams& prm, cudaStream_t st);
+                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, cudaStream_t st);
+
+// ---- backward pass (backward.cu) ----
+// grad2d: 12 zeroed floats per Gaussian row: d mean x,y | d a, d (b+c), d d (a b; c d = -0.5 inverse covariance) |
+// sum of dL/dalpha * alpha | d colour r,g,b | 3 unused.  Accumulated with float atomics.
+int launch_composite_backward(const uint2* ranges, const uint32_t* payload, const float4* rec,
+                              const float* grad_image, const float* aux_t, const uint32_t* aux_n, float* grad2d,
+                              FrameGeom geom, const GsbParams& prm, cudaStream_t st);
+// chain rule through the projection (project.cu's forward, recomputed): grad2d -> the five attribute gradients in
+// the reference layouts (N,3) (N,3) (N,4) (N,3) (N,1); rows without tile instances get zeros.
+int launch_project_backward(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
+                            const uint32_t* depth_key, const uint32_t* count, const float* grad2d, float* g_points,
+                            float* g_scales, float* g_quats, float* g_colors, float* g_opacity, cudaStream_t st);
 
 // egress helpers
 int launch_hwc_to_whc(const float* src_hw3, float* dst_wh3, int width, int height, cudaStream_t st);

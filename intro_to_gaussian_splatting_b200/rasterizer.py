@@ -91,6 +91,26 @@ class Rasterizer:
             check(fn(self._h, C.byref(cam), C.byref(params), _ptr(out), self._stream()), "gsb_render")
         return out
 
+    def render_backward(self, cam: GsbCamera, params: GsbParams, grad_image: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Gradients of the last `render(cam, params)` of this rasterizer (params.save_for_backward must have been
+        1) for dL/d image = grad_image (H,W,3): dict with points (N,3), scales (N,3), quaternions (N,4),
+        colors (N,3), opacity (N,1) -- the reference's attribute names (splat/gaussians.py:19-33)."""
+        H, W = cam.height, cam.width
+        g = _f32c(grad_image)
+        if tuple(g.shape) != (H, W, 3):
+            raise RuntimeError(f"render_backward: grad_image must have shape {(H, W, 3)}, got {tuple(g.shape)}")
+        n, dev = self.n, self.device
+        out = {k: torch.empty((n, w), dtype=torch.float32, device=dev)
+               for k, w in (("points", 3), ("scales", 3), ("quaternions", 4), ("colors", 3), ("opacity", 1))}
+        with torch.cuda.device(self.device):
+            check(self._lib.gsb_render_backward(self._h, C.byref(cam), C.byref(params), _ptr(g),
+                                                *[_ptr(out[k]) for k in ("points", "scales", "quaternions", "colors",
+                                                                         "opacity")], self._stream()),
+                  "gsb_render_backward")
+            if not g.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()  # the host gradient may be a temporary
+        return out
+
     def join_host_copies(self) -> None:
         """Order the current stream after every asynchronous image copy (params.async_host_copy) still in flight."""
         with torch.cuda.device(self.device):

@@ -51,6 +51,7 @@ class Params(C.Structure):
         ("sort_mode", C.c_int32),
         ("collect_stage_times", C.c_int32),
         ("async_host_copy", C.c_int32),
+        ("save_for_backward", C.c_int32),
     ]
 
 

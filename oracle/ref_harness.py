@@ -31,6 +31,7 @@ import sys
 import tempfile
 import types
 
+import numpy as np
 import torch
 
 REFERENCE_ROOT = os.environ.get("GSB_REFERENCE_ROOT", "/root/reference")
@@ -129,3 +130,28 @@ def reference_render_image(ref_scene, image_idx: int, tile_size: int = 16) -> to
     """The parity target: GaussianScene.render_image (splat/gaussian_scene.py:200-238), (W,H,3)."""
     with torch.no_grad(), stable_argsort():
         return ref_scene.render_image(image_idx, tile_size=tile_size)
+
+
+def reference_preprocess_gradients(ref_scene, image_idx: int, seed: int = 0):
+    """Autograd of the UNMODIFIED reference through GaussianScene.preprocess (differentiable torch code,
+    splat/gaussian_scene.py:70-144): L = sum(w_p * points) + sum(w_i * inverse_covariance_2d) + sum(w_o *
+    sigmoid_opacity) + sum(w_c * colors), with the weights drawn per depth-sorted output row from
+    numpy default_rng(seed) in that order (float64 standard normals, cast to fp32).
+    -> (dict of weights, dict of gradients wrt points / scales / quaternions / colors / opacity)."""
+    g = ref_scene.gaussians
+    names = ("points", "scales", "quaternions", "colors", "opacity")
+    for k in names:
+        setattr(g, k, getattr(g, k).detach().clone().requires_grad_(True))
+    with stable_argsort():
+        pp = ref_scene.preprocess(image_idx)
+    rng = np.random.default_rng(seed)
+    m = pp.points.shape[0]
+    w = dict(points=rng.standard_normal((m, 2)), inverse_covariance_2d=rng.standard_normal((m, 2, 2)),
+             sigmoid_opacity=rng.standard_normal((m, 1)), colors=rng.standard_normal((m, 3)))
+    w = {k: v.astype(np.float32) for k, v in w.items()}
+    loss = sum((getattr(pp, k) * torch.from_numpy(v)).sum() for k, v in w.items())
+    loss.backward()
+    grads = {k: getattr(g, k).grad.detach().numpy().copy() for k in names}
+    for k in names:
+        setattr(g, k, getattr(g, k).detach())
+    return w, grads

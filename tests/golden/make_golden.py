@@ -14,6 +14,11 @@ synthetic scenes of intro_to_gaussian_splatting_b200/synth.py, driven through or
   tiles_<scene>.npz       what render_image handed to render_tile: per tile (x_min, y_min, count) and
                           the concatenated row indices (into the depth-sorted arrays)  (:208-237)
   render_<scene>.npz      GaussianScene.render_image output, (W,H,3) fp32  (:200-238)
+  preprocess_grad_<scene>.npz  the REFERENCE'S OWN autograd through GaussianScene.preprocess: weights w_* of a
+                          random linear loss over (points, inverse_covariance_2d, sigmoid_opacity, colors) and
+                          its gradients g_* wrt points / scales / quaternions / colors / opacity
+                          (oracle/ref_harness.py: reference_preprocess_gradients); pins the projection half of
+                          oracle/backward_oracle.py
   hashes.json             sha256 of the raw bytes of each PreprocessedScene field for the big
                           configs (cfg2, cfg3 at full size), where storing the arrays is too large
 """
@@ -125,6 +130,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"tiles_{name}.npz"), view=idx, tiles=tiles, rows=rows)
         np.savez_compressed(os.path.join(HERE, f"render_{name}.npz"), view=idx, image_wh3=img)
         meta["timings_s"][f"render_image_{name}"] = round(dt, 2)
+        if name in ("tiny", "small"):
+            w, g = rh.reference_preprocess_gradients(rh.build_reference_scene(sc), idx, seed=7)
+            np.savez_compressed(os.path.join(HERE, f"preprocess_grad_{name}.npz"), view=idx, seed=7,
+                                **{f"w_{k}": v for k, v in w.items()}, **{f"g_{k}": v for k, v in g.items()})
         print(name, "render_image", f"{dt:.1f}s", img.shape, float(img.max()), flush=True)
 
     for name in ("cfg2", "cfg3"):

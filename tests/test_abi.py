@@ -30,7 +30,7 @@ def test_header_and_library_agree():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.GsbCamera) == 16 * 4 * 2 + 4 * 4 + 2 * 4
-    assert C.sizeof(_lib.GsbParams) == 13 * 4
+    assert C.sizeof(_lib.GsbParams) == 14 * 4
     assert C.sizeof(_lib.GsbFrameInfo) == 3 * 8 + 6 * 4
 
 

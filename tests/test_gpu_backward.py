@@ -1,0 +1,136 @@
+"""GPU parity of gsb_render_backward against oracle/backward_oracle.py, the float64
+autograd restatement of the reference's forward (its projection half is pinned to the reference's own autograd,
+tests/test_backward_oracle.py).  Tolerance (floating point, stated here): every gradient array within
+2e-3 of the oracle in norm, and element-wise within 1e-2*|ref| + 1e-3*max|ref| -- the CUDA side is fp32 with
+ex2.approx and float atomics, the oracle float64."""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from intro_to_gaussian_splatting_b200 import Rasterizer, _lib, render_differentiable
+from intro_to_gaussian_splatting_b200.synth import SceneSpec
+from oracle import backward_oracle as bo
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DENSE = SceneSpec("grad_dense", 260, 64, 48, box=2.5, log_scale_range=(-3.6, -1.6))
+WIDE = SceneSpec("grad_wide", 500, 80, 80, box=5.0, log_scale_range=(-4.0, -1.0), focal_frac=0.5)
+# every Gaussian covers the image centre: lists of 300 (three staging batches) and early termination on ~5 % of pixels
+THICK = SceneSpec("grad_thick", 300, 48, 48, box=0.8, log_scale_range=(-2.5, -1.0))
+NAMES = ("points", "scales", "quaternions", "colors", "opacity")
+
+
+def _setup(spec, full_cover):
+    sc, images, _ = helpers.scene_and_images(spec)
+    cam = images[sorted(images)[0]].pack()
+    prm = _lib.default_params(full_cover=full_cover, save_for_backward=1)
+    return sc, cam, prm
+
+
+def _oracle(sc, cam, prm, gi):
+    ocam, oprm = helpers.to_oracle_camera(cam), helpers.to_oracle_params(prm)
+    arrs = [a.numpy() for a in helpers.scene_arrays(sc)]
+    fr = orc.render(ocam, oprm, *arrs)
+    _, grads = bo.gradients(ocam, oprm, arrs, gi, fr.ranges, fr.sorted_payload, fr.ntx, fr.nty)
+    return fr, grads
+
+
+def _close(got, ref, name):
+    got = got.detach().cpu().numpy().astype(np.float64)
+    assert got.shape == ref.shape, name
+    assert np.isfinite(got).all(), name
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref)
+    assert (err <= 1e-2 * np.abs(ref) + 1e-3 * scale + 1e-9).all(), (name, float(err.max()), float(scale))
+    assert np.linalg.norm(got - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-9, name
+
+
+@pytest.mark.parametrize("spec,full_cover", [("tiny", 1), (DENSE, 1), (DENSE, 0), (WIDE, 1), (THICK, 1), ("small", 1)],
+                         ids=["tiny", "dense", "dense_refgrid", "wide_clamped", "thick_terminating", "small"])
+def test_gradients_match_oracle(spec, full_cover):
+    sc, cam, prm = _setup(spec, full_cover)
+    rng = np.random.default_rng(11)
+    gi = rng.standard_normal((cam.height, cam.width, 3)).astype(np.float32)
+    fr, ref = _oracle(sc, cam, prm, gi)
+    r = Rasterizer(0)
+    r.upload(*[a.cuda() for a in helpers.scene_arrays(sc)])
+    img = r.render(cam, prm)
+    assert np.abs(img.cpu().numpy() - fr.image).max() <= 1e-4  # save_for_backward does not change the image
+    got = r.render_backward(cam, prm, torch.from_numpy(gi).cuda())
+    assert max(np.abs(v).max() for v in ref.values()) > 0
+    for k in NAMES:
+        _close(got[k], ref[k], k)
+    r.close()
+
+
+def test_host_buffers_and_repeatability():
+    sc, cam, prm = _setup(DENSE, 1)
+    gi = torch.from_numpy(np.random.default_rng(5).standard_normal((cam.height, cam.width, 3)).astype(np.float32))
+    r = Rasterizer(0)
+    r.upload(*helpers.scene_arrays(sc))  # host tensors
+    r.render(cam, prm)
+    a = r.render_backward(cam, prm, gi)            # host gradient image
+    b = r.render_backward(cam, prm, gi.cuda())     # may be called again for the same frame
+    for k in NAMES:
+        ref = a[k].double()
+        # float atomics: the order of the sums is not fixed, the values agree to rounding
+        assert (a[k] - b[k]).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-12, k
+    r.close()
+
+
+def test_backward_needs_a_saved_frame():
+    sc, cam, prm = _setup("tiny", 1)
+    gi = torch.zeros((cam.height, cam.width, 3), device="cuda")
+    r = Rasterizer(0)
+    r.upload(*helpers.scene_arrays(sc))
+    with pytest.raises(RuntimeError, match="saved"):
+        r.render_backward(cam, prm, gi)                      # nothing rendered
+    r.render(cam, _lib.default_params(full_cover=1))
+    with pytest.raises(RuntimeError, match="saved"):
+        r.render_backward(cam, prm, gi)                      # rendered without save_for_backward
+    r.render(cam, prm)
+    r.render_backward(cam, prm, gi)
+    other = _lib.default_params(full_cover=0, save_for_backward=1)
+    with pytest.raises(RuntimeError, match="saved"):
+        r.render_backward(cam, other, gi)                    # different params
+    r.upload(*helpers.scene_arrays(sc))
+    with pytest.raises(RuntimeError, match="saved"):
+        r.render_backward(cam, prm, gi)                      # scene replaced since
+    with pytest.raises(RuntimeError, match="shape"):
+        r.render_backward(cam, prm, gi[:-1])
+    r.close()
+
+
+def test_autograd_function_and_descent():
+    """render_differentiable: the torch-facing training step.  Fit colours and opacities of a perturbed copy to
+    the image of the original; plain gradient descent must lower the loss."""
+    sc, cam, _ = _setup(DENSE, 1)
+    prm = _lib.default_params(full_cover=1)
+    dev = torch.device("cuda", 0)
+    pts, scl, qts, col, opa = [a.to(dev) for a in helpers.scene_arrays(sc)]
+    r = Rasterizer(0)
+    with torch.no_grad():
+        r.upload(pts, scl, qts, col, opa)
+        target = r.render(cam, prm).clone()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    col2 = (col + 0.2 * torch.randn(col.shape, generator=g).to(dev)).clamp(0, 1).requires_grad_(True)
+    opa2 = (opa + 0.5 * torch.randn(opa.shape, generator=g).to(dev)).requires_grad_(True)
+    pts2 = pts.clone().requires_grad_(True)
+    losses = []
+    for _ in range(12):
+        img = render_differentiable(r, cam, pts2, scl, qts, col2, opa2, prm)
+        loss = ((img - target) ** 2).mean()
+        for t in (col2, opa2, pts2):
+            t.grad = None
+        loss.backward()
+        assert scl.grad is None and pts2.grad is not None and opa2.grad.shape == opa2.shape
+        with torch.no_grad():
+            col2 -= 40.0 * col2.grad
+            opa2 -= 40.0 * opa2.grad
+        losses.append(loss.item())
+    assert losses[0] > 1e-5
+    assert losses[-1] < 0.5 * losses[0], losses
+    r.close()
