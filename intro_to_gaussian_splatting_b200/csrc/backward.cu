@@ -47,18 +47,31 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+
+// One butterfly step over a PAIR of values: afterwards the lanes whose `bit` is clear hold x summed over the lane
+// pair (L, L ^ bit), the lanes whose bit is set hold y -- one shuffle for two values instead of two.
+__device__ __forceinline__ float pair_step(float x, float y, int lane, int bit) {
+  const bool up = (lane & bit) != 0;
+  const float keep = up ? y : x, send = up ? x : y;
+  return keep + __shfl_xor_sync(0xffffffffu, send, bit);
+}
+__device__ __forceinline__ float single_step(float x, int bit) { return x + __shfl_xor_sync(0xffffffffu, x, bit); }
 
 // Per pixel, with C = sum_j c_j alpha_j T_j and T_{j+1} = T_j (1 - alpha_j) over the blended prefix [0, n):
 //   dL/dc_j     = alpha_j T_j g                                  (g = dL/dC of the pixel)
-//   dL/dalpha_j = T_j ((c_j - A_j) . g),   A_j = sum_{k>j} c_k alpha_k T_k / T_{j+1}
-//   A_{j-1}     = alpha_j c_j + (1 - alpha_j) A_j                (A_{n-1} = 0: nothing behind, no background)
+//   dL/dalpha_j = T_j (c_j . g - B_j),   B_j = (sum_{k>j} c_k alpha_k T_k / T_{j+1}) . g   (a scalar per pixel)
+//   B_{j-1}     = B_j + alpha_j (c_j . g - B_j)                  (B_{n-1} = 0: nothing behind, no background)
 //   alpha = op2 exp(power), power = a dx^2 + (b + c) dx dy + d dy^2, (a b; c d) = -0.5 inverse covariance,
-//   (dx, dy) = mean - pixel  =>  dL/dpower = dL/dalpha * alpha  (and dL/dop2 = that sum / op2).
+//   (dx, dy) = mean - pixel  =>  dL/dpower = dL/dalpha * alpha = (alpha T)(c . g - B)  (and dL/dop2 = sum / op2).
+// A thread's four pixels share dx, so the five geometric sums come from three moments of dL/dpower over dy:
+//   P0 = sum dpw, P1 = sum dpw dy, P2 = sum dpw dy^2:
+//   d a = dx^2 P0, d(b+c) = dx P1, d d = P2, d mx = 2 a dx P0 + (b+c) P1, d my = (b+c) dx P0 + 2 d P1.
+// The nine per-Gaussian sums of a warp are reduced with a 12-shuffle butterfly (pair_step), stored to the warp's
+// row of a shared accumulator, and after each batch of 128 Gaussians the two warps' rows are added into grad2d
+// with three vector reductions per Gaussian (REDG.ADD.F32x4 x2 + one scalar) instead of 18 scalar atomics.
 __global__ void __launch_bounds__(kBwdThreads)
 composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
                           const float4* __restrict__ rec, const float* __restrict__ grad_image,
@@ -66,6 +79,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
                           float* __restrict__ grad2d, const __grid_constant__ BwdArgs a) {
   __shared__ __align__(16) float4 sm[2][kBwdBatch * 3];
   __shared__ uint32_t sm_idx[2][kBwdBatch];
+  __shared__ float sm_acc[2][kBwdBatch * 9];  // [warp][slot][value]; zero except between a batch and its flush
   __shared__ uint32_t sm_nmax[2];
 
   const int tile = blockIdx.x;
@@ -80,7 +94,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
   const uint32_t* pl = payload + rg.x;
 
   // per-pixel state
-  float T[4], gr[4], gg[4], gb[4], Ar[4], Ag[4], Ab[4], fy[4];
+  float T[4], gr[4], gg[4], gb[4], B[4], fy[4];
   uint32_t npx[4];
   uint32_t nw = 0;
 #pragma unroll
@@ -94,15 +108,21 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
     gr[k] = in ? grad_image[3 * p] : 0.f;
     gg[k] = in ? grad_image[3 * p + 1] : 0.f;
     gb[k] = in ? grad_image[3 * p + 2] : 0.f;
-    Ar[k] = Ag[k] = Ab[k] = 0.f;
+    B[k] = 0.f;
     nw = max(nw, npx[k]);
   }
   nw = __reduce_max_sync(0xffffffffu, nw);  // the warp's deepest blended Gaussian + 1
   if (lane == 0) sm_nmax[warp] = nw;
+  for (int s = tid; s < 2 * kBwdBatch * 9; s += kBwdThreads) (&sm_acc[0][0])[s] = 0.f;
   __syncthreads();
   const uint32_t nmax = max(sm_nmax[0], sm_nmax[1]);
   if (nmax == 0) return;
   const int nb = (int)((nmax + kBwdBatch - 1) / kBwdBatch);
+
+  // where the butterfly leaves the totals: value 8 in the lanes with bit 1 set, value 4*b2 + 2*b3 + b4 elsewhere
+  const int v_idx = (lane & 2) ? 8 : ((lane >> 2) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1);
+  const bool v_writer = (lane & 1) == 0 && ((lane & 2) == 0 || lane == 2);
+  float* my_acc = sm_acc[warp] + v_idx;
 
   uint32_t idx[kBwdPerThread];
   auto load_idx = [&](int b) {
@@ -132,7 +152,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
   for (int b = nb - 1; b >= 0; --b) {
     const int buf = b & 1;
     cp_async_wait_all();
-    __syncthreads();  // batch b visible; everyone is done with the other buffer
+    __syncthreads();  // batch b visible; everyone is done with the other buffer and with the last flush
     if (b > 0) {
       stage(buf ^ 1);
       if (b > 1) load_idx(b - 2);
@@ -147,40 +167,56 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
       const float2 q2 = *reinterpret_cast<const float2*>(&sm[buf][i * 3 + 2]);  // g, b
       const float dx = q0.x - fx;
       const float bc = q0.w + q1.x;
-      const float adx = q0.z * dx, bcdx = bc * dx;
-      const float dxx = dx * dx;
-      float s_mx = 0.f, s_my = 0.f, s_a = 0.f, s_bc = 0.f, s_d = 0.f, s_pw = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
-      bool any = false;
+      const float adx = q0.z * dx, bcdx = bc * dx, adxx = adx * dx;
+      float P0 = 0.f, P1 = 0.f, P2 = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f, amax = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float dy = q0.y - fy[k];
-        const float pw = fmaf(fmaf(q1.y, dy, bcdx), dy, adx * dx);  // a dx^2 + (b+c) dx dy + d dy^2
+        const float pw = fmaf(fmaf(q1.y, dy, bcdx), dy, adxx);  // a dx^2 + (b+c) dx dy + d dy^2
         float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z));
         al = (j < npx[k]) ? al : 0.f;  // not blended for this pixel: alpha = 0 makes every update below a no-op
-        any |= al != 0.f;
-        const float om = 1.f - al;
-        T[k] = __fdividef(T[k], om);  // T_j from T_{j+1}
+        amax = fmaxf(amax, al);
+        T[k] = __fdividef(T[k], 1.f - al);  // T_j from T_{j+1}
         const float w = al * T[k];
         s_r = fmaf(w, gr[k], s_r); s_g = fmaf(w, gg[k], s_g); s_b = fmaf(w, gb[k], s_b);
-        const float er = q1.w - Ar[k], eg = q2.x - Ag[k], eb = q2.y - Ab[k];
-        const float dal = T[k] * fmaf(er, gr[k], fmaf(eg, gg[k], eb * gb[k]));
-        Ar[k] = fmaf(al, er, Ar[k]); Ag[k] = fmaf(al, eg, Ag[k]); Ab[k] = fmaf(al, eb, Ab[k]);
-        const float dpw = dal * al;
-        s_pw += dpw;
-        s_a = fmaf(dpw, dxx, s_a);
-        s_bc = fmaf(dpw * dx, dy, s_bc);
-        s_d = fmaf(dpw * dy, dy, s_d);
-        s_mx = fmaf(dpw, fmaf(bc, dy, 2.f * adx), s_mx);
-        s_my = fmaf(dpw, fmaf(2.f * q1.y, dy, bcdx), s_my);
+        const float e = fmaf(q1.w, gr[k], fmaf(q2.x, gg[k], q2.y * gb[k])) - B[k];
+        const float dpw = w * e;
+        B[k] = fmaf(al, e, B[k]);
+        const float t = dpw * dy;
+        P0 += dpw; P1 += t; P2 = fmaf(t, dy, P2);
       }
-      if (!__any_sync(0xffffffffu, any)) continue;  // exp underflow everywhere: every sum is exactly zero
-      s_mx = warp_sum(s_mx); s_my = warp_sum(s_my); s_a = warp_sum(s_a); s_bc = warp_sum(s_bc); s_d = warp_sum(s_d);
-      s_pw = warp_sum(s_pw); s_r = warp_sum(s_r); s_g = warp_sum(s_g); s_b = warp_sum(s_b);
-      if (lane < 9) {
-        const float v = lane == 0 ? s_mx : lane == 1 ? s_my : lane == 2 ? s_a : lane == 3 ? s_bc : lane == 4 ? s_d
-                      : lane == 5 ? s_pw : lane == 6 ? s_r : lane == 7 ? s_g : s_b;
-        atomicAdd(grad2d + (size_t)sm_idx[buf][i] * kG2 + lane, v);
+      if (!__any_sync(0xffffffffu, amax != 0.f)) continue;  // exp underflow everywhere: every sum is exactly zero
+      const float s_a = dx * dx * P0, s_bc = dx * P1;
+      const float s_mx = fmaf(bc, P1, 2.f * adx * P0);
+      const float s_my = fmaf(bcdx, P0, 2.f * q1.y * P1);
+      // butterfly: (mx,my) (a,bc) (d,pw) (r,g) | b
+      float a0 = pair_step(s_mx, s_my, lane, 16), a1 = pair_step(s_a, s_bc, lane, 16);
+      float a2 = pair_step(P2, P0, lane, 16), a3 = pair_step(s_r, s_g, lane, 16), a4 = single_step(s_b, 16);
+      float b0 = pair_step(a0, a1, lane, 8), b1 = pair_step(a2, a3, lane, 8), b2 = single_step(a4, 8);
+      float c0 = pair_step(b0, b1, lane, 4), c1 = single_step(b2, 4);
+      float d0 = pair_step(c0, c1, lane, 2);
+      d0 = single_step(d0, 1);
+      if (v_writer) my_acc[i * 9] = d0;
+    }
+    __syncthreads();  // both warps are done with the batch: flush its sums
+#pragma unroll
+    for (int jj = 0; jj < kBwdPerThread; ++jj) {
+      const int s = jj * kBwdThreads + tid;
+      const uint32_t g = sm_idx[buf][s];
+      if (g == 0xFFFFFFFFu) continue;
+      float v[9];
+      bool nz = false;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        v[q] = sm_acc[0][s * 9 + q] + sm_acc[1][s * 9 + q];
+        sm_acc[0][s * 9 + q] = 0.f; sm_acc[1][s * 9 + q] = 0.f;
+        nz |= v[q] != 0.f;
       }
+      if (!nz) continue;
+      float* dst = grad2d + (size_t)g * kG2;
+      red_add_v4(dst, v[0], v[1], v[2], v[3]);
+      red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
+      atomicAdd(dst + 8, v[8]);
     }
   }
 }
