@@ -350,6 +350,25 @@ def run_ours(args):
     torch.cuda.synchronize()
     frame_latency_ms = sum(a.elapsed_time(b) for a, b in lat_ev) / K
 
+    # the training step, outside the headline's timed region: forward with
+    # save_for_backward + gsb_render_backward for a random dL/d image, serial frames, L2 flushed before each
+    prm_b = _lib.default_params(full_cover=args.full_cover, sort_mode=prm.sort_mode, save_for_backward=1)
+    gimg = torch.randn_like(img)
+    nb_ = min(K, 20)
+    tr_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(nb_)]
+    for s in range(-2, nb_):  # two untimed iterations size the gradient scratch
+        v = views[s % len(views)]
+        flush.zero_()
+        e = tr_ev[max(s, 0)]
+        e[0].record()
+        rast.render(cams[v], prm_b, out=img)
+        e[1].record()
+        rast.render_backward(cams[v], prm_b, gimg)
+        e[2].record()
+    torch.cuda.synchronize()
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in tr_ev) / nb_
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in tr_ev) / nb_
+
     # per-stage times for the roofline (separate loop: the event pairs add a little overhead)
     stage_ms = {k: 0.0 for k in _lib.STAGE_NAMES}
     stage_ms_first = None
@@ -431,6 +450,10 @@ def run_ours(args):
         "launches_per_step": launches / K,
         "roofline": roofline,
         "clocks": clocks,
+        "train_step": {"forward_ms": round(fwd_ms, 4), "backward_ms": round(bwd_ms, 4),
+                       "steps_per_s": round(1e3 / (fwd_ms + bwd_ms), 1), "frames": nb_,
+                       "note": "gsb_render(save_for_backward) + gsb_render_backward, serial frames, rank 0, not part "
+                               "of `value`; gradients wrt all five attribute tensors"},
     }
 
     if world == 1 and not args.no_cpu_baseline:

@@ -11,6 +11,7 @@ from .gaussians import Gaussians  # noqa: F401
 from .image import GaussianImage  # noqa: F401
 from .rasterizer import Rasterizer, ViewRenderer  # noqa: F401
 from .schema import BasicPointCloud, PreprocessedScene  # noqa: F401
+from .train import fit  # noqa: F401
 
 __all__ = ["GaussianScene", "Gaussians", "GaussianImage", "Rasterizer", "ViewRenderer", "PreprocessedScene",
-           "BasicPointCloud", "render_differentiable"]
+           "BasicPointCloud", "render_differentiable", "fit"]

@@ -69,8 +69,10 @@ class Rasterizer:
             if t.is_cuda and t.device != self.device:
                 raise RuntimeError("gsb_upload: tensors live on a different GPU than the rasterizer")
         with torch.cuda.device(self.device):
+            # device tensors (and float/contiguous temporaries of them) are consumed by a kernel on the current
+            # stream, which is the order torch's allocator already respects; host tensors are copied to a staging
+            # block and synchronised inside gsb_upload -- no synchronisation is needed here
             check(self._lib.gsb_upload(self._h, n, *[_ptr(t) for t in ts], self._stream()), "gsb_upload")
-            torch.cuda.current_stream(self.device).synchronize()  # inputs may be temporaries
         self.n = n
 
     # ---- rendering ---------------------------------------------------------------------------

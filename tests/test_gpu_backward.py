@@ -134,3 +134,32 @@ def test_autograd_function_and_descent():
     assert losses[0] > 1e-5
     assert losses[-1] < 0.5 * losses[0], losses
     r.close()
+
+
+def test_fit_two_views():
+    """train.fit: Adam over two orbit views; starting from perturbed colours / opacities / positions the loss to
+    the original's images must fall, and the trained tensors land back on the container."""
+    from types import SimpleNamespace
+
+    from intro_to_gaussian_splatting_b200 import fit
+
+    sc, images, _ = helpers.scene_and_images(DENSE, n_views=2)
+    cams = [images[i].pack() for i in sorted(images)]
+    prm = _lib.default_params(full_cover=1)
+    pts, scl, qts, col, opa = helpers.scene_arrays(sc)
+    r = Rasterizer(0)
+    r.upload(pts, scl, qts, col, opa)
+    targets = [r.render(c, prm).clone() for c in cams]
+    g = torch.Generator().manual_seed(1)
+    gs = SimpleNamespace(points=pts + 0.01 * torch.randn(pts.shape, generator=g), scales=scl.clone(),
+                         quaternions=qts.clone(), colors=(col + 0.2 * torch.randn(col.shape, generator=g)).clamp(0, 1),
+                         opacity=opa + 0.5 * torch.randn(opa.shape, generator=g))
+    hist = fit(gs, cams, targets, steps=60, params=prm, rasterizer=r,
+               lr={"points": 2e-3, "colors": 2e-2, "opacity": 5e-2}, trainable=("points", "colors", "opacity"))
+    assert len(hist) == 60
+    first, last = sum(hist[:2]) / 2, sum(hist[-2:]) / 2
+    assert last < 0.3 * first, (first, last)
+    assert gs.colors.is_cuda and gs.colors.requires_grad and not gs.scales.requires_grad
+    with pytest.raises(ValueError):
+        fit(gs, cams, targets[:1], steps=1, rasterizer=r)
+    r.close()
