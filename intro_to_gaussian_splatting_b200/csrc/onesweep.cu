@@ -192,9 +192,10 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kItems; ++i) peers[i] = match_digit(digit_fast(key[i], shift, mask), bits);
-  // Running per-digit count of this warp: a plain load + store by the group leader.  Warp instructions reach
-  // shared memory in program order, so item i+1 sees item i's update; `volatile` keeps the compiler from
-  // reordering the accesses.
+  // Running per-digit count of this warp: a plain load + store by the group leader (one leader per digit and
+  // item, so no two lanes touch the same counter inside an item).  __syncwarp() orders item i's stores before
+  // item i+1's loads -- a different lane may lead the same digit there; `volatile` keeps the compiler from
+  // caching the counters in registers.
   volatile uint32_t* wcnt = s_cnt[warp];
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
@@ -204,6 +205,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
       pos[i] = wcnt[d];
       wcnt[d] = pos[i] + (uint32_t)__popc(peers[i]);
     }
+    __syncwarp();
   }
 #pragma unroll
   for (int i = 0; i < kItems; ++i)
