@@ -163,3 +163,50 @@ def test_fit_two_views():
     with pytest.raises(ValueError):
         fit(gs, cams, targets[:1], steps=1, rasterizer=r)
     r.close()
+
+
+def test_full_size_properties_cfg2():
+    """Config 2 (100 k Gaussians, 800x800) is far beyond what the float64 oracle can differentiate, so the backward
+    is checked through properties that hold at any size, using the CUDA forward itself:
+      * linearity in dL/dimage:  backward(2 g1 - 3 g2) = 2 backward(g1) - 3 backward(g2);
+      * the image is LINEAR in the colours, so <grad_colors, d> must equal L(colors + d) - L(colors) (to rounding);
+      * directional derivatives along random directions of opacity and position match central differences of the
+        rendered loss (fp32 forward: 2 % tolerance)."""
+    sc, cam, prm = _setup("cfg2", 1)
+    dev = torch.device("cuda", 0)
+    pts, scl, qts, col, opa = [a.to(dev) for a in helpers.scene_arrays(sc)]
+    H, W = cam.height, cam.width
+    gen = torch.Generator(device="cpu").manual_seed(4)
+    g1 = torch.randn((H, W, 3), generator=gen).to(dev)
+    g2 = torch.randn((H, W, 3), generator=gen).to(dev)
+    r = Rasterizer(0)
+
+    def loss(p=pts, c=col, o=opa, g=g1):
+        r.upload(p, scl, qts, c, o)
+        return (r.render(cam, prm).double() * g.double()).sum().item()
+
+    r.upload(pts, scl, qts, col, opa)
+    r.render(cam, prm)
+    b1 = r.render_backward(cam, prm, g1)
+    b2 = r.render_backward(cam, prm, g2)
+    b12 = r.render_backward(cam, prm, 2 * g1 - 3 * g2)
+    for k in NAMES:
+        want = 2 * b1[k].double() - 3 * b2[k].double()
+        scale = want.abs().max().item()
+        assert (b12[k].double() - want).abs().max().item() <= 2e-4 * scale + 1e-12, k
+        assert scale > 0, k
+
+    d_col = 0.05 * torch.randn(col.shape, generator=gen).to(dev)
+    lin = (b1["colors"].double() * d_col.double()).sum().item()
+    fd = loss(c=col + d_col) - loss()
+    assert abs(fd - lin) <= 2e-3 * abs(lin) + 1e-3, (fd, lin)
+
+    for name, base, eps in (("opacity", opa, 2e-2), ("points", pts, 2e-4)):
+        d = torch.randn(base.shape, generator=gen).to(dev)
+        ana = (b1[name].double() * d.double()).sum().item()
+        kw_p = {"o" if name == "opacity" else "p": base + eps * d}
+        kw_m = {"o" if name == "opacity" else "p": base - eps * d}
+        fd = (loss(**kw_p) - loss(**kw_m)) / (2 * eps)
+        assert abs(fd - ana) <= 2e-2 * abs(ana) + 1e-2 * (b1[name].double().norm().item() * d.double().norm().item()) * 1e-2, \
+            (name, fd, ana)
+    r.close()
