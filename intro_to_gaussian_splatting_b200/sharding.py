@@ -6,6 +6,10 @@ Every rank holds the whole Gaussian set (56 B/Gaussian: 336 MB at 6 M, trivial n
 it is broadcast ONCE from rank 0 with `torch.distributed` (NCCL over NVLink/NVSwitch on GPUs, gloo in
 the CPU tests) and there is NO per-frame collective.  Splitting a single frame across GPUs is not
 done: compositing is order dependent and a frame is ~1 ms.
+
+Training is the one place with a real exchange step: with the views sharded, every
+rank differentiates its own view and the five gradient arrays are summed across ranks -- ONE packed (N,14)
+all-reduce per step (`allreduce_gradients`; 56 B/Gaussian), after which every rank applies the same update.
 """
 
 from __future__ import annotations
@@ -54,6 +58,25 @@ def broadcast_gaussians(arrays: Optional[Sequence[torch.Tensor]], n: int, device
         out.append(packed[:, c:c + w].contiguous())
         c += w
     return out
+
+
+def allreduce_gradients(grads: Sequence[Optional[torch.Tensor]], world: int, average: bool = True) -> None:
+    """In place: every non-None tensor of `grads` (same shapes on every rank) becomes the sum -- or the mean --
+    over ranks.  One collective: the tensors are packed into a single flat buffer, reduced, and unpacked."""
+    if world == 1:
+        return
+    live = [g for g in grads if g is not None]
+    if not live:
+        return
+    flat = torch.cat([g.reshape(-1).float() for g in live])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat /= world
+    c = 0
+    for g in live:
+        k = g.numel()
+        g.copy_(flat[c:c + k].reshape(g.shape))
+        c += k
 
 
 def gather_frames(frames: Sequence[torch.Tensor], shard: ViewShard) -> Optional[List[torch.Tensor]]:

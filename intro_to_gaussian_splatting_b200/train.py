@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import GsbCamera, GsbParams
 from .autograd import render_differentiable
 from .rasterizer import Rasterizer
+from .sharding import ViewShard, allreduce_gradients
 
 ATTRIBUTES = ("points", "scales", "quaternions", "colors", "opacity")
 
@@ -25,11 +26,17 @@ def l2_loss(image: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 def fit(gaussians, cameras: Sequence[GsbCamera], targets: Sequence[torch.Tensor], steps: int,
         lr: Optional[Dict[str, float]] = None, params: Optional[GsbParams] = None,
         loss_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor] = l2_loss,
-        rasterizer: Optional[Rasterizer] = None, trainable: Iterable[str] = ATTRIBUTES) -> List[float]:
+        rasterizer: Optional[Rasterizer] = None, trainable: Iterable[str] = ATTRIBUTES,
+        shard: Optional[ViewShard] = None) -> List[float]:
     """Optimise the attribute tensors of `gaussians` (an object with .points .scales .quaternions .colors
     .opacity, e.g. `Gaussians`) so that view k renders like targets[k] ((H,W,3) fp32).  One view per step,
     round-robin; Adam with per-attribute learning rates.  The tensors are replaced by trained leaves on the
-    rasterizer's device.  Returns the loss of every step."""
+    rasterizer's device.  Returns the loss of every step.
+
+    `shard` (view-sharded data parallelism, torch.distributed initialised, every rank starting from the same
+    Gaussians): at step s rank r differentiates view shard.view_of_step(s) -- R different views per step -- and the
+    gradients are averaged with one packed all-reduce, so all ranks apply the same update; the returned losses
+    are this rank's."""
     rast = rasterizer or Rasterizer()
     dev = rast.device
     rates = {"points": 1.6e-4, "scales": 5e-3, "quaternions": 1e-3, "colors": 2.5e-3, "opacity": 5e-2}
@@ -49,12 +56,14 @@ def fit(gaussians, cameras: Sequence[GsbCamera], targets: Sequence[torch.Tensor]
     prm = params or _lib.default_params()
     history: List[float] = []
     for step in range(int(steps)):
-        v = step % len(cameras)
+        v = step % len(cameras) if shard is None else shard.view_of_step(step) % len(cameras)
         opt.zero_grad(set_to_none=True)
         img = render_differentiable(rast, cameras[v], leaves["points"], leaves["scales"], leaves["quaternions"],
                                     leaves["colors"], leaves["opacity"], prm)
         loss = loss_fn(img, tg[v])
         loss.backward()
+        if shard is not None and shard.world > 1:
+            allreduce_gradients([leaves[k].grad for k in ATTRIBUTES if k in trainable], shard.world)
         opt.step()
         history.append(float(loss.detach()))
     for k in ATTRIBUTES:

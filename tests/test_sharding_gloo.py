@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from intro_to_gaussian_splatting_b200.sharding import ViewShard, broadcast_gaussians, gather_frames
+from intro_to_gaussian_splatting_b200.sharding import (ViewShard, allreduce_gradients, broadcast_gaussians,
+                                                      gather_frames)
 from intro_to_gaussian_splatting_b200.synth import make_scene
 
 
@@ -50,6 +51,17 @@ def _worker(rank, world, port, q):
         allf = gather_frames(frames, sh)
         if rank == 0:
             ok = ok and [float(f[0, 0, 0]) for f in allf] == [float(v) for v in range(7)]
+        # the training exchange: five gradient arrays (one of them absent), one packed all-reduce, mean over ranks
+        shapes = [(n, 3), (n, 3), (n, 4), (n, 3), (n, 1)]
+        grads = [torch.full(sh_, float(rank + 1) * (i + 1)) for i, sh_ in enumerate(shapes)]
+        grads[1] = None
+        allreduce_gradients(grads, world)
+        for i, g in enumerate(grads):
+            if g is not None:
+                ok = ok and tuple(g.shape) == shapes[i] and bool((g == 1.5 * (i + 1)).all())
+        summed = [torch.full((4, 2), float(rank + 1))]
+        allreduce_gradients(summed, world, average=False)
+        ok = ok and bool((summed[0] == 3.0).all())
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
