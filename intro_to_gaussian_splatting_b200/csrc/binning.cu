@@ -27,14 +27,22 @@ __device__ __forceinline__ void st_relaxed64(uint64_t* p, uint64_t v) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// emit: output-parallel expansion.  A block owns 256 consecutive Gaussians (in emission order) and
-// walks ITS OUTPUT RANGE in aligned groups of four slots per thread: one binary search over the block's
-// 256 offsets (shared memory) and one division locate the first slot of a group, the other three follow
-// by stepping through the rect (and on to the next Gaussian), and a full group leaves as 16/32-byte
-// vector stores.  A Gaussian covering 2 000 tiles costs the same per key as one covering 4.
-//   kCombined = false (FULL):  keys[o] = tile << 32 | depth bits,  payload[o] = Gaussian index
-//   kCombined = true  (SPLIT): keys[o] = tile << 32 | Gaussian index  (depth order is the emission order;
-//                              the radix passes sort the tile field only and carry the index inside the key)
+// emit: output-parallel, load-balanced expansion.  A block owns kEmitChunk consecutive OUTPUT slots, whatever
+// Gaussians they belong to: two warps locate the first and last Gaussian of the chunk with a 32-way search of the
+// offsets array (4-5 rounds of one coalesced probe per lane), the block stages those Gaussians (offset, index,
+// rect) in shared memory in windows of kEmitWindow, and every thread fills aligned groups of four slots: one
+// binary search in shared memory and one division locate the first slot of a group, the other three follow by
+// stepping through the rect (and on to the next Gaussian); a full group leaves as one 16/32-byte vector store.
+// A Gaussian covering 2 000 tiles costs the same per key as one covering 4, and a block of near, huge Gaussians
+// costs the same as a block of far, tiny ones (blocks that own 256 GAUSSIANS do not: in depth order the first
+// blocks emit 100x more than the last; measured 110 us vs 36 us once the tile-less Gaussians moved to the end).
+//   kKind = kEmitFull    (FULL):  keys[o] = tile << 32 | depth bits,  payload[o] = Gaussian index
+//   kKind = kEmitSplit64 (SPLIT): keys[o] = tile << 32 | Gaussian index  (depth order is the emission order;
+//                                 the radix passes sort the tile field only and carry the index inside the key)
+//   kKind = kEmitSplit32 (SPLIT): 32-bit keys[o] = tile << rank_bits | emission position.  The projection keys
+//                                 Gaussians without tiles to the end of the depth order, so the position of an
+//                                 emitting Gaussian is < V and rank_bits = ceil(log2 V); chosen by the host when
+//                                 tile bits + rank_bits <= 32 -- half the bytes through every radix pass.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
@@ -127,95 +135,160 @@ int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t
   return (int)cudaGetLastError();
 }
 
-template <bool kCombined>
+enum EmitKind { kEmitFull = 0, kEmitSplit64 = 1, kEmitSplit32 = 2 };
+#ifndef GSB_EMIT_CHUNK
+#define GSB_EMIT_CHUNK 8192
+#endif
+constexpr int kEmitChunk = GSB_EMIT_CHUNK;   // output slots per block
+constexpr int kEmitWindow = 512;   // Gaussians staged per window
+constexpr uint32_t kEmitRun = 16;  // consecutive output slots per thread and search
+
+template <int kKind>
 __global__ void __launch_bounds__(kEmitThreads)
 emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
             int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
-            uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
-  __shared__ uint32_t s_off[kEmitThreads + 1];
-  __shared__ uint32_t s_gid[kEmitThreads];
-  __shared__ uint32_t s_low[kEmitThreads];  // low key word: depth bits (FULL) or Gaussian index (SPLIT)
-  __shared__ ushort4 s_rect[kEmitThreads];
-  const int64_t base = (int64_t)blockIdx.x * kEmitThreads;
-  const int64_t i = base + threadIdx.x;
-  uint32_t off = 0;
-  if (i < n) {
-    const uint32_t g = perm ? perm[i] : (uint32_t)i;
-    off = offsets[i];
-    s_gid[threadIdx.x] = g;
-    s_low[threadIdx.x] = kCombined ? g : depth_key[g];
-    s_rect[threadIdx.x] = rect[g];
-  }
+            int rank_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+  constexpr bool kCombined = kKind != kEmitFull;
+  __shared__ uint32_t s_off[kEmitWindow + 1];
+  __shared__ uint32_t s_gid[kEmitWindow];
+  __shared__ uint32_t s_low[kEmitWindow];  // low key word: depth bits (FULL), Gaussian index or emission position
+  __shared__ ushort4 s_rect[kEmitWindow];
+  __shared__ int64_t s_bound[2];
   const uint32_t k_total = *total;
-  s_off[threadIdx.x] = (i < n) ? off : k_total;
-  if (threadIdx.x == 0) {
-    const int64_t nxt = base + kEmitThreads;
-    s_off[kEmitThreads] = (nxt < n) ? offsets[nxt] : k_total;
+  const uint32_t c0 = blockIdx.x * (uint32_t)kEmitChunk;
+  if (c0 >= k_total) return;
+  const uint32_t c1 = (k_total - c0 > (uint32_t)kEmitChunk) ? c0 + kEmitChunk : k_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 2) {
+    // largest i with offsets[i] <= target (equal offsets = Gaussians without tiles: the last one wins, i.e. the one
+    // that emits).  Invariant: offsets[lo] <= target < offsets[hi], with the virtual offsets[n] = K.
+    const uint32_t target = warp == 0 ? c0 : c1 - 1u;
+    int64_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const int64_t step = (hi - lo + 32) / 33;
+      const int64_t p = lo + (int64_t)(lane + 1) * step;
+      const bool le = p < hi && offsets[p] <= target;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, le));  // monotone: the first cnt lanes
+      const int64_t nhi = lo + (int64_t)(cnt + 1) * step;
+      lo += (int64_t)cnt * step;
+      hi = nhi < hi ? nhi : hi;
+    }
+    if (lane == 0) s_bound[warp] = lo;
   }
   __syncthreads();
-  const uint32_t begin = s_off[0], end = s_off[kEmitThreads];
-  for (uint32_t o4 = (begin & ~3u) + 4u * threadIdx.x; o4 < end; o4 += 4u * kEmitThreads) {
-    const uint32_t first = o4 > begin ? o4 : begin;
-    const uint32_t last = (o4 + 4u < end) ? o4 + 4u : end;  // exclusive
-    if (first >= last) continue;
-    // largest j with s_off[j] <= first  (entries with count 0 share their successor's offset and lose)
-    int lo = 0, hi = kEmitThreads;  // invariant: s_off[lo] <= first < s_off[hi]
-#pragma unroll
-    for (int step = 0; step < 8; ++step) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= first) lo = mid; else hi = mid;
+  const int64_t g0 = s_bound[0], g1 = s_bound[1];
+  for (int64_t w0 = g0; w0 <= g1; w0 += kEmitWindow) {
+    const int cntw = (int)((g1 - w0 + 1 < (int64_t)kEmitWindow) ? g1 - w0 + 1 : (int64_t)kEmitWindow);
+    if (w0 != g0) __syncthreads();  // everyone is done with the previous window
+    for (int j = threadIdx.x; j < cntw; j += kEmitThreads) {
+      const int64_t i = w0 + j;
+      const uint32_t g = perm ? perm[i] : (uint32_t)i;
+      s_off[j] = offsets[i];
+      s_gid[j] = g;
+      s_low[j] = kKind == kEmitSplit32 ? (uint32_t)i : (kKind == kEmitSplit64 ? g : depth_key[g]);
+      s_rect[j] = rect[g];
     }
-    ushort4 r = s_rect[lo];
-    uint32_t nxt_off = s_off[lo + 1];
-    const uint32_t t = first - s_off[lo];
-    const uint32_t w = (uint32_t)r.y - (uint32_t)r.x + 1u;
-    uint32_t ty = (uint32_t)r.z + t / w;
-    uint32_t tx = (uint32_t)r.x + t % w;
-    uint64_t kv[4];
-    uint32_t pv[4];
+    if (threadIdx.x == 0) s_off[cntw] = (w0 + cntw < n) ? offsets[w0 + cntw] : k_total;
+    __syncthreads();
+    const uint32_t begin = s_off[0] > c0 ? s_off[0] : c0;
+    const uint32_t end = s_off[cntw] < c1 ? s_off[cntw] : c1;
+    // a thread owns kEmitRun consecutive slots (four aligned groups of four): ONE search and one division, then it
+    // steps through rects; a warp's stores cover 32 * kEmitRun consecutive slots
+    for (uint32_t o16 = (begin & ~(kEmitRun - 1u)) + kEmitRun * threadIdx.x; o16 < end; o16 += kEmitRun * kEmitThreads) {
+      const uint32_t first = o16 > begin ? o16 : begin;
+      const uint32_t last = (o16 + kEmitRun < end) ? o16 + kEmitRun : end;  // exclusive
+      if (first >= last) continue;
+      // largest j with s_off[j] <= first  (entries with count 0 share their successor's offset and lose)
+      int lo = 0, hi = cntw;  // invariant: s_off[lo] <= first < s_off[hi]
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t slot = o4 + q;
-      kv[q] = 0; pv[q] = 0;
-      if (slot >= first && slot < last) {
-        while (slot >= nxt_off) {  // move on to the next Gaussian with a non-empty rect
-          ++lo;
-          nxt_off = s_off[lo + 1];
-          r = s_rect[lo];
-          tx = r.x; ty = r.z;
-        }
-        kv[q] = ((uint64_t)(ty * (uint32_t)tiles_x + tx) << 32) | (uint64_t)s_low[lo];
-        pv[q] = s_gid[lo];
-        if (++tx > (uint32_t)r.y) { tx = r.x; ++ty; }
+      for (int step = 0; step < 9; ++step) {  // 2^9 = kEmitWindow
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= first) lo = mid; else hi = mid;
       }
-    }
-    if (first == o4 && last == o4 + 4u) {
-      ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + o4);  // o4 % 4 == 0: 32-byte aligned
-      kp[0] = make_ulonglong2(kv[0], kv[1]);
-      kp[1] = make_ulonglong2(kv[2], kv[3]);
-      if (!kCombined) *reinterpret_cast<uint4*>(payload + o4) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
-    } else {
+      ushort4 r = s_rect[lo];
+      uint32_t nxt_off = s_off[lo + 1];
+      const uint32_t t = first - s_off[lo];
+      const uint32_t w = (uint32_t)r.y - (uint32_t)r.x + 1u;
+      uint32_t ty = (uint32_t)r.z + t / w;
+      uint32_t tx = (uint32_t)r.x + t % w;
+      uint32_t low = s_low[lo], gid = s_gid[lo];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t slot = o4 + q;
-        if (slot >= first && slot < last) {
-          keys[slot] = kv[q];
-          if (!kCombined) payload[slot] = pv[q];
+      for (uint32_t o4 = o16; o4 < o16 + kEmitRun; o4 += 4u) {
+        if (o4 + 4u <= first || o4 >= last) continue;
+        uint32_t tv[4], lv[4], pv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t slot = o4 + q;
+          tv[q] = 0; lv[q] = 0; pv[q] = 0;
+          if (slot >= first && slot < last) {
+            while (slot >= nxt_off) {  // move on to the next Gaussian with a non-empty rect
+              ++lo;
+              nxt_off = s_off[lo + 1];
+              r = s_rect[lo];
+              low = s_low[lo]; gid = s_gid[lo];
+              tx = r.x; ty = r.z;
+            }
+            tv[q] = ty * (uint32_t)tiles_x + tx;
+            lv[q] = low;
+            pv[q] = gid;
+            if (++tx > (uint32_t)r.y) { tx = r.x; ++ty; }
+          }
+        }
+        const bool whole = o4 >= first && o4 + 4u <= last;
+        if (kKind == kEmitSplit32) {
+          // 32-bit keys: tile << rank_bits | emission position
+          uint32_t* k32 = reinterpret_cast<uint32_t*>(keys);
+          uint32_t v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = (tv[q] << rank_bits) | lv[q];
+          if (whole) {
+            *reinterpret_cast<uint4*>(k32 + o4) = make_uint4(v[0], v[1], v[2], v[3]);  // o4 % 4 == 0: 16-byte aligned
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t slot = o4 + q;
+              if (slot >= first && slot < last) k32[slot] = v[q];
+            }
+          }
+        } else {
+          uint64_t kv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) kv[q] = ((uint64_t)tv[q] << 32) | (uint64_t)lv[q];
+          if (whole) {
+            ulonglong2* kp = reinterpret_cast<ulonglong2*>(keys + o4);  // o4 % 4 == 0: 32-byte aligned
+            kp[0] = make_ulonglong2(kv[0], kv[1]);
+            kp[1] = make_ulonglong2(kv[2], kv[3]);
+            if (!kCombined) *reinterpret_cast<uint4*>(payload + o4) = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t slot = o4 + q;
+              if (slot >= first && slot < last) {
+                keys[slot] = kv[q];
+                if (!kCombined) payload[slot] = pv[q];
+              }
+            }
+          }
         }
       }
     }
   }
 }
 
-int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
-                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
-                uint32_t* payload, cudaStream_t st) {
-  if (n == 0) return 0;
-  unsigned blocks = (unsigned)((n + kEmitThreads - 1) / kEmitThreads);
-  if (combined)
-    emit_kernel<true><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
+int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n, int64_t k,
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, int rank_bits,
+                uint64_t* keys, uint32_t* payload, cudaStream_t st) {
+  if (n == 0 || k <= 0) return 0;
+  unsigned blocks = (unsigned)((k + kEmitChunk - 1) / kEmitChunk);
+  if (combined && rank_bits > 0)
+    emit_kernel<kEmitSplit32><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x,
+                                                               rank_bits, keys, payload);
+  else if (combined)
+    emit_kernel<kEmitSplit64><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, 0,
+                                                               keys, payload);
   else
-    emit_kernel<false><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, keys, payload);
+    emit_kernel<kEmitFull><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, 0, keys,
+                                                            payload);
   return (int)cudaGetLastError();
 }
 
@@ -515,6 +588,7 @@ tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, 
       // Mailbox in mapped pinned host memory: the host polls word 4 and learns M and K while the depth sort is
       // still running on the main stream, so the read-back it needs to size the key buffers costs no bubble.
       host_mailbox[0] = *m_counter;
+      host_mailbox[1] = m_counter[kCtlVisible];  // V: Gaussians with tiles (sizes the rank field of 32-bit keys)
       host_mailbox[2] = (uint32_t)total64;
       host_mailbox[3] = (uint32_t)(total64 >> 32);
       __threadfence_system();

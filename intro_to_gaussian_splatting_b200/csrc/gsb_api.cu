@@ -95,6 +95,10 @@ struct GsbContext {
   DevBuf image, image2, scratch;
   // save_for_backward: per-pixel blended count / final transmittance of the last frame; gradient scratch
   DevBuf aux_t, aux_n, grad2d, grad_stage;
+  bool allow_keys32 = true;
+  bool frame_projected = false;  // last frame came from render_device: last_cam / last_prm describe its projection
+  GsbCamera last_cam{};
+  GsbParams last_prm{};
   bool have_saved = false;
   GsbCamera saved_cam{};
   GsbParams saved_prm{};
@@ -172,7 +176,9 @@ int launch_stats_async(GsbContext* c, FrameGeom geom, uint32_t* ctl, const CtlLa
 
 // Wait for tile_stats_kernel's mailbox (M, K) without draining the main stream: the depth-sort passes queued
 // behind the projection keep running while the host sizes the key buffers and queues emit / sort / composite.
-int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t st, int64_t* m, int64_t* k) {
+int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t st, int64_t* m, int64_t* k,
+                int64_t* v = nullptr) {
+  if (v) *v = 0;
   if (tiles <= 0) {  // no tile grid, no tile_stats launch: plain read-back of M, K = 0
     GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 4, cudaMemcpyDeviceToHost, st));
     GSB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -192,6 +198,7 @@ int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t 
   }
   *m = box[0];
   *k = (int64_t)(((uint64_t)box[3] << 32) | box[2]);
+  if (v) *v = box[1];
   return GSB_OK;
 }
 
@@ -217,8 +224,12 @@ int depth_sort(GsbContext* c, int64_t n, const uint32_t* hist, uint32_t* control
 // everything after the per-Gaussian records exist: tile stats -> scan -> K -> emit -> sort.
 // `n_rows` per-Gaussian rows; `perm` optional emission order; `low_bits_sorted`: emission order already
 // sorts the low key word (SPLIT mode / pre-sorted rows), so only the tile digits need radix passes.
-int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, FrameGeom geom,
-                 uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches) {
+// `rows_with_tiles`: upper bound of the emission positions that emit anything when the HOST knows one
+// (pre-sorted rows: M), -1 when the projection counted it (V, read from the mailbox).
+// With low_bits_sorted the keys shrink to 32 bits -- tile << rank_bits | emission position -- whenever
+// ceil(log2 tiles) + ceil(log2 V) <= 32 (config 3: 13 + 19); the last radix pass then writes perm[position].
+int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, int64_t rows_with_tiles,
+                 FrameGeom geom, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
   GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
   GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl + L.scan, st));
@@ -226,12 +237,13 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   tm.mark(GSB_STAGE_SCAN);
   // tile stats were launched on the auxiliary stream right after the projection (they do not depend on the
   // depth sort) and post M and K to the host mailbox; pick them up without draining the main stream
-  int64_t m = 0, k = 0;
-  GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k));
+  int64_t m = 0, k = 0, v = 0;
+  GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k, &v));
   GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // ranges / tile histograms are inputs of what follows
   if (k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
   c->info.m_in_view = m;
   c->info.k_instances = k;
+  if (rows_with_tiles >= 0) v = rows_with_tiles;
 
   GSB_TRY(c->keys_a.ensure((size_t)k * 8 + 8));
   GSB_TRY(c->keys_b.ensure((size_t)k * 8 + 8));
@@ -239,27 +251,49 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   GSB_TRY(c->vals_b.ensure((size_t)k * 4 + 4));
 
   const int tile_bits = ceil_log2(tiles);
-  SortPlan plan = low_bits_sorted ? make_sort_plan<uint64_t>(k, 32, 32 + tile_bits)
-                                  : make_sort_plan<uint64_t>(k, 0, 32 + tile_bits);
-  GSB_TRY(c->control2.ensure(plan.control_words * 4));
-  GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
-
-  plan.keys_only = low_bits_sorted ? 1 : 0;
-  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 2, n_rows, c->depth_key.as<uint32_t>(),
-                                        c->rect.as<ushort4>(), geom.tiles_x, /*combined=*/low_bits_sorted,
-                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
-  ++*launches;
-  tm.mark(GSB_STAGE_EMIT);
-  bool in_a = true;
+  const int rank_bits = ceil_log2(v);
+  const bool keys32 = low_bits_sorted && c->allow_keys32 && tile_bits + rank_bits <= 32;
   const uint32_t* hist = ctl + L.hist + (low_bits_sorted ? 4 * kRadix : 0);
-  GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
-                                                  c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
-                                                  c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(), hist,
-                                                  c->control2.as<uint32_t>(), &in_a, launches, st));
+  bool in_a = true;
+  int passes = 0;
+  if (keys32) {
+    SortPlan plan = make_sort_plan<uint32_t>(k, rank_bits, rank_bits + tile_bits);
+    plan.keys_only = 1;
+    plan.low_bits = rank_bits;
+    plan.gather_table = perm;  // nullptr (pre-sorted rows): the position IS the row
+    GSB_TRY(c->control2.ensure(plan.control_words * 4));
+    GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+    GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 2, n_rows, k, c->depth_key.as<uint32_t>(),
+                                          c->rect.as<ushort4>(), geom.tiles_x, true, rank_bits,
+                                          c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
+    if (n_rows > 0 && k > 0) ++*launches;
+    tm.mark(GSB_STAGE_EMIT);
+    GSB_CUDA_TRY((cudaError_t)launch_sort<uint32_t>(plan, c->keys_a.as<uint32_t>(), nullptr, c->keys_a.as<uint32_t>(),
+                                                    c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(),
+                                                    c->vals_b.as<uint32_t>(), hist, c->control2.as<uint32_t>(), &in_a,
+                                                    launches, st));
+    passes = plan.passes;
+  } else {
+    SortPlan plan = low_bits_sorted ? make_sort_plan<uint64_t>(k, 32, 32 + tile_bits)
+                                    : make_sort_plan<uint64_t>(k, 0, 32 + tile_bits);
+    GSB_TRY(c->control2.ensure(plan.control_words * 4));
+    GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+    plan.keys_only = low_bits_sorted ? 1 : 0;
+    GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 2, n_rows, k, c->depth_key.as<uint32_t>(),
+                                          c->rect.as<ushort4>(), geom.tiles_x, /*combined=*/low_bits_sorted, 0,
+                                          c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
+    if (n_rows > 0 && k > 0) ++*launches;
+    tm.mark(GSB_STAGE_EMIT);
+    GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
+                                                    c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
+                                                    c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(), hist,
+                                                    c->control2.as<uint32_t>(), &in_a, launches, st));
+    passes = plan.passes;
+  }
   c->keys_materialized = !low_bits_sorted;
   c->sorted_in_a = in_a;
-  c->emitted_valid = (plan.passes <= 1) && !low_bits_sorted;  // one pass: the a-buffers still hold the emitted order
-  c->info.sort_passes = (k > 0) ? plan.passes : 0;
+  c->emitted_valid = (passes <= 1) && !low_bits_sorted;  // one pass: the a-buffers still hold the emitted order
+  c->info.sort_passes = (k > 0) ? passes : 0;
   tm.mark(GSB_STAGE_SORT);
   return GSB_OK;
 }
@@ -324,6 +358,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   const bool split = mode != GSB_SORT_FULL;  // SPLIT and BINNED both sort the depth keys per Gaussian first
   int launches = 0;
   c->have_frame = false;
+  c->frame_projected = false;
   c->have_order = false;
   c->have_saved = false;
   std::memset(&c->info, 0, sizeof(c->info));
@@ -365,7 +400,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   if (mode == GSB_SORT_BINNED) {
     GSB_TRY(bin_by_tile(c, n, perm, geom, ctl, L, st, tm, &launches));
   } else {
-    GSB_TRY(bin_and_sort(c, n, perm, split, geom, ctl, L, st, tm, &launches));
+    GSB_TRY(bin_and_sort(c, n, perm, split, /*rows_with_tiles=*/-1, geom, ctl, L, st, tm, &launches));
   }
 
   if (!prm->full_cover)  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
@@ -388,6 +423,9 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   c->info.kernel_launches = launches;
   c->frame_rows = n;
   c->have_frame = true;
+  c->frame_projected = true;
+  c->last_cam = *cam;
+  c->last_prm = *prm;
   if (prm->save_for_backward) {
     c->have_saved = true;
     c->saved_cam = *cam;
@@ -453,6 +491,8 @@ int gsb_create(GsbContext** out, int device) {
     set_sort_items(e ? std::atoi(e) : 16);
     e = std::getenv("GSB_FORCE_WIDE_STATUS");             // 1: 64-bit look-back words even below 2^30 keys
     set_force_wide_status(e ? std::atoi(e) : 0);
+    e = std::getenv("GSB_KEYS32");                        // 0: never use the 32-bit tile keys of SPLIT mode
+    c->allow_keys32 = !e || std::atoi(e) != 0;
   }
   if (cudaHostAlloc((void**)&c->pinned, 64, cudaHostAllocMapped) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
   std::memset(c->pinned, 0, 64);
@@ -503,6 +543,7 @@ int gsb_upload(GsbContext* c, int64_t n, const float* xyz, const float* scales, 
   cudaStream_t st = (cudaStream_t)stream;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   c->have_frame = false;
+  c->frame_projected = false;
   c->have_saved = false;
   ++c->scene_gen;
   c->n = n;
@@ -660,6 +701,7 @@ int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, in
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   const int64_t n = c->n;
   c->have_frame = false;
+  c->frame_projected = false;
   if (m_out) *m_out = 0;
   if (n == 0) return GSB_OK;
   FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
@@ -729,6 +771,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   const int cover = cu ? 1 : prm.full_cover;  // render.cu covers every pixel (:119-124)
   FrameGeom geom{W, H, tile_grid_dim(W, kTile, cover), tile_grid_dim(H, kTile, cover)};
   c->have_frame = false;
+  c->frame_projected = false;
   c->have_order = false;
   std::memset(&c->info, 0, sizeof(c->info));
   c->info.n = m; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
@@ -769,7 +812,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   if (m > 0) ++launches;
   tm.mark(GSB_STAGE_PROJECT);
   GSB_TRY(launch_stats_async(c, geom, hdr, L, st, &launches));
-  GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, geom, hdr, L, st, tm, &launches));
+  GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, /*rows_with_tiles=*/m, geom, hdr, L, st, tm, &launches));
   c->info.m_in_view = m;
 
   float* dev_image = out_image;
@@ -832,6 +875,23 @@ int gsb_debug_projection(GsbContext* c, uint8_t* in_view, float* depth, float* p
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   const int64_t n = c->frame_rows;
   if (n == 0) return GSB_OK;
+  if (c->frame_projected) {
+    // The frame variant of the projection writes no record for Gaussians without tiles and keys them like culled
+    // ones; the getter reports every in-view row, so run the debug variant once more for the frame's camera
+    // (identical values for the rows the frame did write; the control words it accumulates into are dead by now).
+    FrameGeom geom{c->last_cam.width, c->last_cam.height, c->info.tiles_x, c->info.tiles_y};
+    GSB_TRY(c->dbg_cov2d.ensure((size_t)n * 16));
+    GSB_TRY(c->dbg_conic.ensure((size_t)n * 16));
+    GSB_TRY(c->dbg_bbox.ensure((size_t)n * 16));
+    DebugOut dbg{c->dbg_cov2d.as<float>(), c->dbg_conic.as<float>(), c->dbg_bbox.as<float>()};
+    const CtlLayout L = ctl_layout(geom, n, 0);
+    GSB_TRY(c->control.ensure(L.total * 4));
+    uint32_t* ctl = c->control.as<uint32_t>();
+    GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, c->last_cam, c->last_prm, geom,
+                                             c->depth_key.as<uint32_t>(), c->rec.as<float4>(), c->rect.as<ushort4>(),
+                                             c->count.as<uint32_t>(), ctl, ctl + L.hist, 0,
+                                             reinterpret_cast<int32_t*>(ctl + L.grid), &dbg, 0));
+  }
   // staging: u8[n] (padded to 4) | depth | pxy | radius | rect
   const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
   GSB_TRY(c->scratch.ensure(n4 + (size_t)n * 4 * (1 + 2 + 1 + 4)));

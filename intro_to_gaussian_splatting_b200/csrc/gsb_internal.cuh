@@ -36,6 +36,7 @@ constexpr int kTile = 16;              // pixels per tile edge (the only size th
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
+constexpr int kCtlVisible = 4;  // word of the per-frame control header that counts the Gaussians WITH tiles (V)
 
 // ---- scene planes ----
 enum Plane { PX = 0, PY, PZ, PSX, PSY, PSZ, PQW, PQX, PQY, PQZ, PR, PG, PB, POP, kNumPlanes };
@@ -56,6 +57,8 @@ struct DebugOut {
 int launch_repack(const float* xyz, const float* scales, const float* quats, const float* colors,
                   const float* opacity, float* planes, int64_t n, int64_t n_pad, cudaStream_t st);
 
+// m_counter: the control header -- [0] += M (in view), [kCtlVisible] += V (in view and touching a tile).
+// Without `dbg` (the frame variant) rows that touch no tile get depth_key 0xFFFFFFFF and no record / rect.
 // depth_hist: 4*256 zeroed words (digit histograms of the depth keys; weighted by tile count when
 // hist_weighted).  diff_grid: (tiles_x+1)*(tiles_y+1) zeroed ints (2-D difference grid of the tile rects).
 int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
@@ -75,10 +78,12 @@ size_t scan_status_words(int64_t n);
 int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* status,
                 cudaStream_t st);
 // `total`: device pointer to K (low word).  combined = false: keys = tile<<32 | depth bits, payload = Gaussian
-// index (FULL); combined = true: keys = tile<<32 | Gaussian index, payload untouched (SPLIT, keys-only passes)
-int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
-                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, uint64_t* keys,
-                uint32_t* payload, cudaStream_t st);
+// index (FULL); combined = true: keys = tile<<32 | Gaussian index, payload untouched (SPLIT, keys-only passes);
+// combined with rank_bits > 0: 32-bit keys tile << rank_bits | emission position, written to `keys` as u32[K]
+// k: the host's copy of K (sizes the grid: one block per 8 192 output slots)
+int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n, int64_t k,
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, int rank_bits,
+                uint64_t* keys, uint32_t* payload, cudaStream_t st);
 // debug only: sorted keys tile<<32 | depth bits from ranges + sorted payload (SPLIT mode never stores them)
 int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
                         uint64_t* keys, cudaStream_t st);
@@ -97,7 +102,10 @@ int launch_tile_sort(const uint2* ranges, int tiles, const uint32_t* rank, const
 struct SortPlan {
   int begin_bit, end_bit, passes;
   int items;              // keys per thread (8 or 16)
-  int keys_only;          // 1: payload packed in unsorted key bits; last pass writes low 32 bits to vals
+  int keys_only;          // 1: payload packed in unsorted key bits; the last pass writes, per key, the low
+                          // `low_bits` bits (all 32 when low_bits == 0) -- or gather_table[those bits] -- to vals
+  int low_bits;
+  const uint32_t* gather_table;
   int wide_status;        // 1: 64-bit look-back words (2^30 keys and more)
   int64_t n;
   int64_t tiles;          // onesweep tiles per pass

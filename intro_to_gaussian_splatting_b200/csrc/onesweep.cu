@@ -108,8 +108,10 @@ histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int begin_bit, int en
 //   kPairs            (key, u32 payload) pairs; vals_in == nullptr means "payload = the key's index"
 //                     (first pass of the per-Gaussian depth sort: saves an iota kernel and a key copy)
 //   kKeysOnly         the payload is packed into key bits that are not being sorted (tile<<32 | gaussian)
-//   kKeysOnlyLowOut   same, and only the low 32 bits of each key are written (to vals_out): the last tile
-//                     pass of SPLIT mode, after which nothing reads the tile half of the key any more
+//   kKeysOnlyLowOut   same, and only the packed payload is written (to vals_out): the last tile pass of SPLIT
+//                     mode, after which nothing reads the tile field of the key any more.  The payload is the
+//                     key's low word masked with low_mask; with a table (vals_in, otherwise unused in this mode)
+//                     it is an emission position and table[position] -- the Gaussian index -- is written.
 enum SortMode { kPairs = 0, kKeysOnly = 1, kKeysOnlyLowOut = 2 };
 
 __device__ __forceinline__ uint32_t digit32(uint32_t k, int shift, uint32_t mask) { return (k >> shift) & mask; }
@@ -158,7 +160,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
                                               const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                               uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                                               uint32_t mask, const uint32_t* __restrict__ hist, W* status,
-                                              uint32_t tile, int valid) {
+                                              uint32_t tile, int valid, uint32_t low_mask) {
   using SW = StatusWord<W>;
   constexpr W kWAgg = (W)1 << SW::kShift, kWPre = (W)2 << SW::kShift, kWMask = ((W)1 << SW::kShift) - 1;
   constexpr int kTileKeys = kThreads * kItems;
@@ -314,8 +316,12 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     if (full || j < valid) {
       const KeyT k = exch.keys[j];
       dst[i] = s_gofs[digit_fast(k, shift, mask)] + (uint32_t)j;
-      if constexpr (kMode == kKeysOnlyLowOut) vals_out[dst[i]] = (uint32_t)k;
-      else keys_out[dst[i]] = k;
+      if constexpr (kMode == kKeysOnlyLowOut) {
+        const uint32_t low = (uint32_t)k & low_mask;
+        vals_out[dst[i]] = vals_in ? vals_in[low] : low;
+      } else {
+        keys_out[dst[i]] = k;
+      }
     }
   }
   if constexpr (kMode == kPairs) {
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, kItems == 8 ? 4 : GSB_SORT_MINBLOCKS
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                 uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
                 const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
-                W* status /* [num_tiles][256] */) {
+                W* status /* [num_tiles][256] */, uint32_t low_mask) {
   constexpr int kTileKeys = kThreads * kItems;
   __shared__ SortSmem<KeyT, kItems> sm;
   const int tid = threadIdx.x;
@@ -360,9 +366,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   const int valid = (int)min((int64_t)kTileKeys, n - (int64_t)tile * kTileKeys);
   const uint32_t mask = (1u << bits) - 1u;
   if (valid == kTileKeys)
-    onesweep_tile<KeyT, kItems, kMode, true, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, bits, mask, hist, status, tile, valid);
+    onesweep_tile<KeyT, kItems, kMode, true, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, bits, mask, hist, status, tile, valid, low_mask);
   else
-    onesweep_tile<KeyT, kItems, kMode, false, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, bits, mask, hist, status, tile, valid);
+    onesweep_tile<KeyT, kItems, kMode, false, W>(sm, keys_in, vals_in, keys_out, vals_out, n, shift, bits, mask, hist, status, tile, valid, low_mask);
 }
 
 }  // namespace
@@ -381,6 +387,8 @@ SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
   if (p.passes < 0) p.passes = 0;
   p.n = n;
   p.keys_only = 0;
+  p.low_bits = 0;
+  p.gather_table = nullptr;
   p.items = g_sort_items;
   const int64_t tile_keys = (int64_t)kThreads * p.items;
   p.tiles = (n + tile_keys - 1) / tile_keys;
@@ -408,13 +416,13 @@ template int launch_key_histogram<uint64_t>(const SortPlan&, const uint64_t*, ui
 template <typename KeyT, int kItems, typename W>
 static void launch_pass(int mode, unsigned tiles, cudaStream_t st, const KeyT* kin, const uint32_t* vin, KeyT* kout,
                         uint32_t* vout, int64_t n, int shift, int bits, const uint32_t* hist, uint32_t* ticket,
-                        W* status) {
+                        W* status, uint32_t low_mask) {
   if (mode == kPairs)
-    onesweep_kernel<KeyT, kItems, kPairs, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+    onesweep_kernel<KeyT, kItems, kPairs, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status, low_mask);
   else if (mode == kKeysOnly)
-    onesweep_kernel<KeyT, kItems, kKeysOnly, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+    onesweep_kernel<KeyT, kItems, kKeysOnly, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status, low_mask);
   else
-    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status);
+    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status, low_mask);
 }
 
 template <typename KeyT>
@@ -437,18 +445,20 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
     const size_t per_pass = (size_t)plan.tiles * kRadix;
     const int mode = !plan.keys_only ? kPairs : (p == plan.passes - 1 ? kKeysOnlyLowOut : kKeysOnly);
     const uint32_t* h = hist + (size_t)p * kRadix;
+    const uint32_t low_mask = (plan.low_bits > 0 && plan.low_bits < 32) ? ((1u << plan.low_bits) - 1u) : 0xFFFFFFFFu;
+    if (mode == kKeysOnlyLowOut) vin = plan.gather_table;  // the one keys-only pass that reads `vals_in`: as a table
     if (plan.wide_status) {
       uint64_t* stp = reinterpret_cast<uint64_t*>(status) + (size_t)p * per_pass;  // status starts 8-byte aligned
       if (plan.items == 16)
-        launch_pass<KeyT, 16, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+        launch_pass<KeyT, 16, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
       else
-        launch_pass<KeyT, 8, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+        launch_pass<KeyT, 8, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
     } else {
       uint32_t* stp = status + (size_t)p * per_pass;
       if (plan.items == 16)
-        launch_pass<KeyT, 16, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+        launch_pass<KeyT, 16, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
       else
-        launch_pass<KeyT, 8, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp);
+        launch_pass<KeyT, 8, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
     }
     if (launches) ++*launches;
     kin = kout; vin = vout;

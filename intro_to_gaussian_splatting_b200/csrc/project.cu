@@ -126,12 +126,13 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
                uint32_t* __restrict__ count, uint32_t* __restrict__ m_counter, uint32_t* __restrict__ depth_hist,
                int hist_weighted, int32_t* __restrict__ diff_grid, DebugOut dbg) {
   __shared__ uint32_t s_hist[4][kRadix];
-  __shared__ int s_cnt;
+  __shared__ int s_cnt, s_vis;
   for (int t = threadIdx.x; t < 4 * kRadix; t += blockDim.x) (&s_hist[0][0])[t] = 0;
-  if (threadIdx.x == 0) s_cnt = 0;
+  if (threadIdx.x == 0) { s_cnt = 0; s_vis = 0; }
   __syncthreads();
   const int gw = a.tiles_x + 1;  // width of the difference grid
-  int kept = 0;
+  int kept = 0, with_tiles = 0;
+  uint32_t n_ff = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     bool keep = false;
     uint32_t cnt = 0;
@@ -250,26 +251,34 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       // opacity as the CPU path uses it: sigmoid(sigmoid(logit)) (splat/gaussian_scene.py:143 then :164)
       const float sig1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
       const float op2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sig1)));
-      // conic pre-scaled by -0.5: exact (power of two), so (-0.5*d) @ inv rounds identically (composite.cu)
-      rec[3 * i + 0] = make_float4(px, py, -0.5f * i00, -0.5f * i01);
-      // the blend loop evaluates alpha = op2 * exp(power) as exp2(power*log2e + log2(op2)): one FFMA + MUFU.EX2
-      rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, log2f(op2), cr);
-      rec[3 * i + 2] = make_float4(cg, cb, rad, sig1);
-      rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
-      dkey = __float_as_uint(vz);
+      // A Gaussian that touches no tile is never read again on the render path: the frame variant skips its
+      // record and keys it like a culled one (0xFFFFFFFF), so the depth sort leaves the V Gaussians WITH tiles
+      // first, in depth order.  The debug variant (gsb_preprocess, gsb_debug_projection) keeps every in-view row.
+      if (kDebug || cnt) {
+        // conic pre-scaled by -0.5: exact (power of two), so (-0.5*d) @ inv rounds identically (composite.cu)
+        rec[3 * i + 0] = make_float4(px, py, -0.5f * i00, -0.5f * i01);
+        // the blend loop evaluates alpha = op2 * exp(power) as exp2(power*log2e + log2(op2)): one FFMA + MUFU.EX2
+        rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, log2f(op2), cr);
+        rec[3 * i + 2] = make_float4(cg, cb, rad, sig1);
+        rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
+        dkey = __float_as_uint(vz);
+      }
       if (kDebug) {
         reinterpret_cast<float4*>(dbg.cov2d)[i] = make_float4(ca, cbb, cc, cd);
         reinterpret_cast<float4*>(dbg.conic)[i] = make_float4(i00, i01, i10, i11);
         reinterpret_cast<float4*>(dbg.bbox)[i] = make_float4(mnx, mny, mxx, mxy);
       }
-    } else {
+    } else if (kDebug) {
       rect[i] = make_ushort4(0, 0, 0, 0);
     }
     count[i] = cnt;
     depth_key[i] = dkey;  // 0xFFFFFFFF when culled: sorts behind every real depth (z >= 0.2 > 0, finite)
     kept += keep ? 1 : 0;
+    with_tiles += cnt ? 1 : 0;
     const uint32_t w = hist_weighted ? cnt : 1u;
-    if (w) {
+    if (dkey == 0xFFFFFFFFu) {
+      n_ff += w;  // all four digits are 255: counted per thread, added once per warp (no same-address atomics)
+    } else if (w) {
       atomicAdd(&s_hist[0][dkey & 255u], w);
       atomicAdd(&s_hist[1][(dkey >> 8) & 255u], w);
       atomicAdd(&s_hist[2][(dkey >> 16) & 255u], w);
@@ -282,12 +291,24 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       atomicAdd(&diff_grid[(ty1 + 1) * gw + tx1 + 1], 1);
     }
   }
-  // M = number of in-view Gaussians: one atomic per block
+  // M = number of in-view Gaussians, V = number that touch a tile: one atomic each per block
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
-  if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&s_cnt, kept);
+  for (int o = 16; o > 0; o >>= 1) {
+    kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    with_tiles += __shfl_xor_sync(0xffffffffu, with_tiles, o);
+    n_ff += __shfl_xor_sync(0xffffffffu, n_ff, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (kept) atomicAdd(&s_cnt, kept);
+    if (with_tiles) atomicAdd(&s_vis, with_tiles);
+    if (n_ff) {
+      atomicAdd(&s_hist[0][255], n_ff); atomicAdd(&s_hist[1][255], n_ff);
+      atomicAdd(&s_hist[2][255], n_ff); atomicAdd(&s_hist[3][255], n_ff);
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0 && s_cnt) atomicAdd(m_counter, (uint32_t)s_cnt);
+  if (threadIdx.x == 0 && s_vis) atomicAdd(m_counter + kCtlVisible, (uint32_t)s_vis);
   for (int t = threadIdx.x; t < 4 * kRadix; t += blockDim.x) {
     const uint32_t v = (&s_hist[0][0])[t];
     if (v) atomicAdd(&depth_hist[t], v);

@@ -197,7 +197,10 @@ def test_wide_status_words_and_small_sort_tiles():
     sc, images, _ = scene_and_images("cfg2")
     cam = images[1].pack()
     fr_cache = {}
-    for env in ({"GSB_FORCE_WIDE_STATUS": "1"}, {"GSB_SORT_ITEMS": "8"}, {"GSB_FORCE_WIDE_STATUS": "1", "GSB_SORT_ITEMS": "8"}):
+    # GSB_KEYS32=0: SPLIT mode with the 64-bit tile keys it uses when tile bits + rank bits exceed 32 (the default
+    # contexts of every other test take the 32-bit keys at these sizes)
+    for env in ({"GSB_FORCE_WIDE_STATUS": "1"}, {"GSB_SORT_ITEMS": "8"}, {"GSB_FORCE_WIDE_STATUS": "1", "GSB_SORT_ITEMS": "8"},
+                {"GSB_KEYS32": "0"}, {"GSB_KEYS32": "0", "GSB_FORCE_WIDE_STATUS": "1"}):
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
