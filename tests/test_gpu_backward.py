@@ -210,3 +210,57 @@ def test_full_size_properties_cfg2():
         assert abs(fd - ana) <= 2e-2 * abs(ana) + 1e-2 * (b1[name].double().norm().item() * d.double().norm().item()) * 1e-2, \
             (name, fd, ana)
     r.close()
+
+
+def test_edge_cases():
+    """Nothing to differentiate (empty set, nothing in view), an image that is not a multiple of the tile size under
+    the reference grid (pixels outside the grid carry no gradient), and NULL outputs."""
+    import ctypes as C
+
+    sc, cam, prm = _setup("tiny", 0)
+    r = Rasterizer(0)
+    z = lambda *s: torch.zeros(s)  # noqa: E731
+    gi = torch.ones((cam.height, cam.width, 3), device="cuda")
+    # empty Gaussian set
+    r.upload(z(0, 3), z(0, 3), z(0, 4), z(0, 3), z(0, 1))
+    r.render(cam, prm)
+    g = r.render_backward(cam, prm, gi)
+    assert all(v.shape[0] == 0 for v in g.values())
+    # everything behind the camera: all gradients exactly zero
+    pts, scl, qts, col, opa = helpers.scene_arrays(sc)
+    far = pts.clone()
+    far[:, 2] = -50.0
+    r.upload(far, scl, qts, col, opa)
+    img = r.render(cam, prm)
+    assert float(img.abs().max()) == 0.0
+    g = r.render_backward(cam, prm, gi)
+    assert all(float(v.abs().max()) == 0.0 for v in g.values())
+    # 70x52 image, reference grid (4x3 tiles of 16: columns 64.. and rows 48.. are outside it)
+    from intro_to_gaussian_splatting_b200.synth import SceneSpec
+    odd = SceneSpec("grad_odd", 200, 70, 52, box=2.5, log_scale_range=(-3.6, -1.6))
+    sc2, cam2, prm2 = _setup(odd, 0)
+    gi2 = np.random.default_rng(2).standard_normal((cam2.height, cam2.width, 3)).astype(np.float32)
+    fr, ref = _oracle(sc2, cam2, prm2, gi2)
+    r.upload(*helpers.scene_arrays(sc2))
+    img = r.render(cam2, prm2)
+    assert float(img[:, 64:].abs().max()) == 0.0 and float(img[48:].abs().max()) == 0.0
+    got = r.render_backward(cam2, prm2, torch.from_numpy(gi2).cuda())
+    for k in NAMES:
+        _close(got[k], ref[k], k)
+    # the same with full cover (partial tiles at the right and bottom edges)
+    sc3, cam3, prm3 = _setup(odd, 1)
+    fr3, ref3 = _oracle(sc3, cam3, prm3, gi2)
+    r.render(cam3, prm3)
+    got = r.render_backward(cam3, prm3, torch.from_numpy(gi2).cuda())
+    for k in NAMES:
+        _close(got[k], ref3[k], k)
+    # NULL outputs are allowed (only the colour gradient requested)
+    n = sc3.xyz.shape[0]
+    only = torch.empty((n, 3), device="cuda")
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.gsb_render_backward(r._h, C.byref(cam3), C.byref(prm3), C.c_void_p(torch.from_numpy(gi2).cuda().data_ptr()),
+                                       None, None, None, C.c_void_p(only.data_ptr()), None, st))
+    torch.cuda.synchronize()
+    assert torch.allclose(only, got["colors"], rtol=1e-4, atol=1e-7)
+    r.close()
