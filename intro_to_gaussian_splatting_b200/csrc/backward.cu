@@ -21,6 +21,8 @@
 // This TU is compiled with FMA contraction on: gradients carry a tolerance, not a bit pattern.
 #include <math.h>
 
+#include <type_traits>
+
 #include "gsb_internal.cuh"
 
 namespace gsb {
@@ -96,7 +98,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
   // per-pixel state
   float T[4], gr[4], gg[4], gb[4], B[4], fy[4];
   uint32_t npx[4];
-  uint32_t nw = 0;
+  uint32_t nw = 0, nmin_w = 0xFFFFFFFFu;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int py = py0 + k;
@@ -110,8 +112,10 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
     gb[k] = in ? grad_image[3 * p + 2] : 0.f;
     B[k] = 0.f;
     nw = max(nw, npx[k]);
+    nmin_w = min(nmin_w, npx[k]);
   }
   nw = __reduce_max_sync(0xffffffffu, nw);  // the warp's deepest blended Gaussian + 1
+  nmin_w = __reduce_min_sync(0xffffffffu, nmin_w);  // below this index every pixel of the warp blends
   if (lane == 0) sm_nmax[warp] = nw;
   for (int s = tid; s < 2 * kBwdBatch * 9; s += kBwdThreads) (&sm_acc[0][0])[s] = 0.f;
   __syncthreads();
@@ -160,7 +164,10 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
     // this warp's slots of the batch: [0, hi)
     const int base = b * kBwdBatch;
     const int hi = min((int)nw - base, kBwdBatch);
-    for (int i = hi - 1; i >= 0; --i) {
+    // one Gaussian (slot i of the batch) against the thread's four pixels; kSel: some pixel of the warp stopped
+    // blending before this Gaussian, so alpha is masked per pixel (warp-uniformly false below the warp's minimum)
+    auto step = [&](int i, auto sel_tag) {
+      constexpr bool kSel = decltype(sel_tag)::value;
       const uint32_t j = (uint32_t)(base + i);
       const float4 q0 = sm[buf][i * 3];      // mx, my, a, b
       const float4 q1 = sm[buf][i * 3 + 1];  // c, d, log2(op2), r
@@ -174,7 +181,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
         const float dy = q0.y - fy[k];
         const float pw = fmaf(fmaf(q1.y, dy, bcdx), dy, adxx);  // a dx^2 + (b+c) dx dy + d dy^2
         float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z));
-        al = (j < npx[k]) ? al : 0.f;  // not blended for this pixel: alpha = 0 makes every update below a no-op
+        if (kSel) al = (j < npx[k]) ? al : 0.f;  // not blended for this pixel: alpha = 0 makes every update a no-op
         amax = fmaxf(amax, al);
         T[k] = __fdividef(T[k], 1.f - al);  // T_j from T_{j+1}
         const float w = al * T[k];
@@ -185,7 +192,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
         const float t = dpw * dy;
         P0 += dpw; P1 += t; P2 = fmaf(t, dy, P2);
       }
-      if (!__any_sync(0xffffffffu, amax != 0.f)) continue;  // exp underflow everywhere: every sum is exactly zero
+      if (!__any_sync(0xffffffffu, amax != 0.f)) return;  // exp underflow everywhere: every sum is exactly zero
       const float s_a = dx * dx * P0, s_bc = dx * P1;
       const float s_mx = fmaf(bc, P1, 2.f * adx * P0);
       const float s_my = fmaf(bcdx, P0, 2.f * q1.y * P1);
@@ -197,7 +204,10 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
       float d0 = pair_step(c0, c1, lane, 2);
       d0 = single_step(d0, 1);
       if (v_writer) my_acc[i * 9] = d0;
-    }
+    };
+    int i = hi - 1;
+    for (; i >= 0 && base + i >= (int)nmin_w; --i) step(i, std::true_type{});
+    for (; i >= 0; --i) step(i, std::false_type{});
     __syncthreads();  // both warps are done with the batch: flush its sums
 #pragma unroll
     for (int jj = 0; jj < kBwdPerThread; ++jj) {
