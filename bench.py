@@ -196,16 +196,18 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def stage_bytes(info, n, width, height, split):
-    """Algorithmic HBM bytes per frame and stage.  N Gaussians, M in view, K tile
-    instances, P pixels.  SPLIT: the tile passes move one u64 (tile<<32 | index) per instance and the last
-    pass writes only the 4-byte index."""
+    """Algorithmic HBM bytes per frame and stage.  N Gaussians, M in view, V of them with
+    tiles (not in GsbFrameInfo: M is used, an upper bound), K tile instances, P pixels.  SPLIT: the tile passes
+    move one key per instance -- 4 bytes (tile << rank bits | position) when it fits, else 8 (tile << 32 | index)
+    -- and the last pass writes only the 4-byte Gaussian index."""
     N, M, K = n, int(info.m_in_view), int(info.k_instances)
     P = width * height
     tiles = info.tiles_x * info.tiles_y
     cells = (info.tiles_x + 1) * (info.tiles_y + 1)
+    kb = 4 if int(getattr(info, "key_bits", 64)) == 32 else 8
     if split:
-        sort = (info.sort_passes - 1) * 16 * K + 12 * K      # (8 read + 8 written) per pass, last pass 8 + 4
-        emit = 24 * M + 8 * K
+        sort = (info.sort_passes - 1) * 2 * kb * K + (kb + 4) * K   # key read + written per pass; last pass key in, index out
+        emit = 24 * M + kb * K
     else:
         sort = info.sort_passes * 24 * K                     # (8+4 read, 8+4 written) per pass
         emit = 24 * M + 12 * K

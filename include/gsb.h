@@ -111,7 +111,7 @@ typedef struct GsbFrameInfo {
   int32_t sort_passes; /* onesweep passes executed over the K keys */
   int32_t depth_passes;/* onesweep passes executed over the M depth keys (split mode) */
   int32_t kernel_launches; /* kernels launched by the last gsb_render */
-  int32_t reserved;
+  int32_t key_bits;    /* width of the tile-sort keys of the last frame: 32 or 64 (0: no K-sized sort, BINNED) */
 } GsbFrameInfo;
 
 typedef struct GsbContext GsbContext;

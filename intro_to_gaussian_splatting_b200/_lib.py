@@ -73,7 +73,7 @@ class GsbFrameInfo(C.Structure):
         ("sort_passes", C.c_int32),
         ("depth_passes", C.c_int32),
         ("kernel_launches", C.c_int32),
-        ("reserved", C.c_int32),
+        ("key_bits", C.c_int32),
     ]
 
 

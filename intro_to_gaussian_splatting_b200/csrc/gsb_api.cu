@@ -294,6 +294,7 @@ int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_b
   c->sorted_in_a = in_a;
   c->emitted_valid = (passes <= 1) && !low_bits_sorted;  // one pass: the a-buffers still hold the emitted order
   c->info.sort_passes = (k > 0) ? passes : 0;
+  c->info.key_bits = keys32 ? 32 : 64;
   tm.mark(GSB_STAGE_SORT);
   return GSB_OK;
 }

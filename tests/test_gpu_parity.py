@@ -221,6 +221,8 @@ def test_wide_status_words_and_small_sort_tiles():
                     fr_cache["fr"] = orc.render(to_oracle_camera(cam), to_oracle_params(prm), *scene_arrays(sc))
                 _check_frame_against_oracle(r, fr_cache["fr"], prm)
                 assert np.abs(img.cpu().numpy() - fr_cache["fr"].image).max() <= PIXEL_TOL
+                want_bits = 64 if (sm == _lib.GSB_SORT_FULL or env.get("GSB_KEYS32") == "0") else 32
+                assert r.frame_info().key_bits == want_bits, (env, sm)
             g = torch.Generator().manual_seed(3)
             keys = torch.randint(-(2 ** 62), 2 ** 62, (300_000,), generator=g, dtype=torch.int64)
             vals = torch.arange(300_000, dtype=torch.int32)
