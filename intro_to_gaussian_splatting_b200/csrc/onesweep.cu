@@ -194,20 +194,16 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kItems; ++i) peers[i] = match_digit(digit_fast(key[i], shift, mask), bits);
-  // Running per-digit count of this warp: a plain load + store by the group leader (one leader per digit and
-  // item, so no two lanes touch the same counter inside an item).  __syncwarp() orders item i's stores before
-  // item i+1's loads -- a different lane may lead the same digit there; `volatile` keeps the compiler from
-  // caching the counters in registers.
-  volatile uint32_t* wcnt = s_cnt[warp];
+  // Running per-digit count of this warp, kept by the group leaders (one leader per digit and item) with a
+  // shared-memory atomic that returns the count before this item.  (A plain load + store by the leader is what
+  // the arithmetic needs, but a different lane may lead the same digit in the next item: racecheck rightly flags
+  // that, and ordering it with a __syncwarp() per item measured 6-8 us per frame slower than the atomic.)
+  uint32_t* wcnt = s_cnt[warp];
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     pos[i] = 0;
-    if ((peers[i] & lt_mask) == 0u) {  // lowest lane of its peer group == the leader
-      const uint32_t d = digit_fast(key[i], shift, mask);
-      pos[i] = wcnt[d];
-      wcnt[d] = pos[i] + (uint32_t)__popc(peers[i]);
-    }
-    __syncwarp();
+    if ((peers[i] & lt_mask) == 0u)  // lowest lane of its peer group == the leader
+      pos[i] = atomicAdd(&wcnt[digit_fast(key[i], shift, mask)], (uint32_t)__popc(peers[i]));
   }
 #pragma unroll
   for (int i = 0; i < kItems; ++i)
