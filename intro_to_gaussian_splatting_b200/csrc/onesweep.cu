@@ -124,6 +124,7 @@ __device__ __forceinline__ uint32_t digit64(uint64_t k, int shift, uint32_t mask
 // costs ~30 cycles of a per-SM unit per warp instruction here (clock64 instrumentation: 11 000 of a tile's 23 600
 // cycles went into 16 matches per thread); a ballot costs ~4, so digits narrower than 8 bits get cheaper.
 __device__ __forceinline__ unsigned match_digit(uint32_t d, int bits) {
+#if defined(GSB_MATCH_BITS_CHECK)
   unsigned peers = 0xffffffffu;
 #pragma unroll
   for (int b = 0; b < kRadixBits; ++b) {
@@ -134,6 +135,24 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d, int bits) {
     }
   }
   return peers;
+#else
+  // always kRadixBits ballots: the bits above a narrower digit are zero in every lane and match trivially, which
+  // is cheaper than a (warp-uniform) width test per bit
+  (void)bits;
+  unsigned differ = 0u;  // lanes whose digit differs from mine in some bit
+#pragma unroll
+  for (int b = 0; b < kRadixBits; ++b) {
+    // differ |= ballot(bit) ^ (bit ? ~0 : 0), spelled in PTX so that it stays 4 SASS instructions per bit
+    // (LOP3 -> predicate, VOTE, SEL, LOP3); the C++ form is canonicalised into 6 (shift, and, setp, vote, neg, lop3)
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t, m, s;\n\t"
+        "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "selp.b32 s, 0xffffffff, 0, p;\n\t"
+        "xor.b32 m, m, s;\n\tor.b32 %0, %0, m;\n\t}"
+        : "+r"(differ) : "r"(d), "r"(1u << b));
+  }
+  return ~differ;
+#endif
 }
 
 template <typename KeyT>
