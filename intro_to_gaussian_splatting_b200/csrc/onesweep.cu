@@ -122,37 +122,26 @@ __device__ __forceinline__ uint32_t digit64(uint64_t k, int shift, uint32_t mask
 }
 // Lanes holding the same digit, from one ballot per digit bit.  `__match_any_sync` compiles to MATCH.ANY, which
 // costs ~30 cycles of a per-SM unit per warp instruction here (clock64 instrumentation: 11 000 of a tile's 23 600
-// cycles went into 16 matches per thread); a ballot costs ~4, so digits narrower than 8 bits get cheaper.
+// cycles went into 16 matches per thread); a ballot costs ~4.
 __device__ __forceinline__ unsigned match_digit(uint32_t d, int bits) {
-#if defined(GSB_MATCH_BITS_CHECK)
-  unsigned peers = 0xffffffffu;
-#pragma unroll
-  for (int b = 0; b < kRadixBits; ++b) {
-    if (b < bits) {  // warp-uniform
-      const bool bit = (d >> b) & 1u;
-      const unsigned m = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? m : ~m;
-    }
-  }
-  return peers;
-#else
-  // always kRadixBits ballots: the bits above a narrower digit are zero in every lane and match trivially, which
-  // is cheaper than a (warp-uniform) width test per bit
-  (void)bits;
   unsigned differ = 0u;  // lanes whose digit differs from mine in some bit
-#pragma unroll
-  for (int b = 0; b < kRadixBits; ++b) {
-    // differ |= ballot(bit) ^ (bit ? ~0 : 0), spelled in PTX so that it stays 4 SASS instructions per bit
-    // (LOP3 -> predicate, VOTE, SEL, LOP3); the C++ form is canonicalised into 6 (shift, and, setp, vote, neg, lop3)
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 t, m, s;\n\t"
-        "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
-        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
-        "selp.b32 s, 0xffffffff, 0, p;\n\t"
-        "xor.b32 m, m, s;\n\tor.b32 %0, %0, m;\n\t}"
-        : "+r"(differ) : "r"(d), "r"(1u << b));
+  // differ |= ballot(bit) ^ (bit ? ~0 : 0), spelled in PTX so that it stays ~3 SASS instructions per bit (one R2P
+  // for seven predicates, VOTE, predicated complement, 3-input ORs); the C++ form is canonicalised into 6 per bit
+#define GSB_MATCH_BIT(B)                                                           \
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t, m, s;\n\t"                               \
+      "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"                              \
+      "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"                                 \
+      "selp.b32 s, 0xffffffff, 0, p;\n\t"                                          \
+      "xor.b32 m, m, s;\n\tor.b32 %0, %0, m;\n\t}"                                  \
+      : "+r"(differ) : "r"(d), "r"(1u << (B)))
+  if (bits > 5) {  // warp-uniform.  Two complete sequences: splitting one into 5 + 3 bits costs the 8-bit passes 13 %
+    GSB_MATCH_BIT(0); GSB_MATCH_BIT(1); GSB_MATCH_BIT(2); GSB_MATCH_BIT(3); GSB_MATCH_BIT(4);
+    GSB_MATCH_BIT(5); GSB_MATCH_BIT(6); GSB_MATCH_BIT(7);
+  } else {         // the bits above a narrow digit are zero in every lane and would match trivially
+    GSB_MATCH_BIT(0); GSB_MATCH_BIT(1); GSB_MATCH_BIT(2); GSB_MATCH_BIT(3); GSB_MATCH_BIT(4);
   }
+#undef GSB_MATCH_BIT
   return ~differ;
-#endif
 }
 
 template <typename KeyT>
@@ -244,7 +233,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     // padding keys (all ones) sit in the highest used bin and, being last in tile order, last in it
     real = sum;
     if ((uint32_t)d == mask) real -= (uint32_t)(kTileKeys - valid);
-    SW::st(st, (tile == 0 ? kWPre : kWAgg) | (W)real);
+    if ((uint32_t)d <= mask) SW::st(st, (tile == 0 ? kWPre : kWAgg) | (W)real);  // bins above a narrow digit stay empty
 
     // block-wide exclusive scans: local tile counts (-> smem layout) and the global histogram (-> bin bases)
     uint32_t a = sum, b = hist[d];
@@ -283,7 +272,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   //     were measured slower: most of this phase is spent WAITING for a slow predecessor's aggregate, not walking.)
   {
     uint32_t excl = 0;
-    if (tile != 0) {
+    if (tile != 0 && (uint32_t)tid <= mask) {  // a 5-bit pass has 32 live digits: only warp 0 looks back
       const W* col = status + tid;  // status is [tile][256]
       int64_t t = (int64_t)tile - 1;
       bool found = false;
