@@ -220,6 +220,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
 
   // 4a. thread d owns digit d: scan the warp counters, publish the tile's aggregate as early as possible
   uint32_t real, tile_start, bin_base;
+  bool bin_live;
   W* st = status + (size_t)tile * kRadix + tid;
   {
     const int d = tid;
@@ -233,10 +234,14 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     // padding keys (all ones) sit in the highest used bin and, being last in tile order, last in it
     real = sum;
     if ((uint32_t)d == mask) real -= (uint32_t)(kTileKeys - valid);
-    if ((uint32_t)d <= mask) SW::st(st, (tile == 0 ? kWPre : kWAgg) | (W)real);  // bins above a narrow digit stay empty
+    // bins above a narrow digit's mask, and bins that are empty in the whole array (known from the histogram:
+    // e.g. all but a handful of exponent bytes in the last depth pass), take no part in the look-back
+    const uint32_t b_hist = hist[d];
+    bin_live = (uint32_t)d <= mask && b_hist != 0u;
+    if (bin_live) SW::st(st, (tile == 0 ? kWPre : kWAgg) | (W)real);
 
     // block-wide exclusive scans: local tile counts (-> smem layout) and the global histogram (-> bin bases)
-    uint32_t a = sum, b = hist[d];
+    uint32_t a = sum, b = b_hist;
     const uint32_t a_in = a, b_in = b;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -272,7 +277,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   //     were measured slower: most of this phase is spent WAITING for a slow predecessor's aggregate, not walking.)
   {
     uint32_t excl = 0;
-    if (tile != 0 && (uint32_t)tid <= mask) {  // a 5-bit pass has 32 live digits: only warp 0 looks back
+    if (tile != 0 && bin_live) {  // e.g. a 5-bit pass has 32 live digits: only warp 0 looks back
       const W* col = status + tid;  // status is [tile][256]
       int64_t t = (int64_t)tile - 1;
       bool found = false;

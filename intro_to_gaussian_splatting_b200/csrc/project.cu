@@ -148,8 +148,6 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       const float sx = planes[PSX * n_pad + i], sy = planes[PSY * n_pad + i], sz = planes[PSZ * n_pad + i];
       float q0 = planes[PQW * n_pad + i], q1 = planes[PQX * n_pad + i], q2 = planes[PQY * n_pad + i],
             q3 = planes[PQZ * n_pad + i];
-      const float cr = planes[PR * n_pad + i], cg = planes[PG * n_pad + i], cb = planes[PB * n_pad + i];
-      const float logit = planes[POP * n_pad + i];
 
       const float vx = rowvec_col(x, y, z, V, 0);
       const float vy = rowvec_col(x, y, z, V, 1);
@@ -248,13 +246,16 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       tile_interval(mny, mxy, a.tile_size, a.tiles_y, ty0, ty1);
       if (tx1 >= tx0 && ty1 >= ty0) cnt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
 
-      // opacity as the CPU path uses it: sigmoid(sigmoid(logit)) (splat/gaussian_scene.py:143 then :164)
-      const float sig1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
-      const float op2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sig1)));
       // A Gaussian that touches no tile is never read again on the render path: the frame variant skips its
       // record and keys it like a culled one (0xFFFFFFFF), so the depth sort leaves the V Gaussians WITH tiles
       // first, in depth order.  The debug variant (gsb_preprocess, gsb_debug_projection) keeps every in-view row.
       if (kDebug || cnt) {
+        // colour and opacity are only read (and the two sigmoids only evaluated) for Gaussians that are drawn
+        const float cr = planes[PR * n_pad + i], cg = planes[PG * n_pad + i], cb = planes[PB * n_pad + i];
+        const float logit = planes[POP * n_pad + i];
+        // opacity as the CPU path uses it: sigmoid(sigmoid(logit)) (splat/gaussian_scene.py:143 then :164)
+        const float sig1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-logit)));
+        const float op2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-sig1)));
         // conic pre-scaled by -0.5: exact (power of two), so (-0.5*d) @ inv rounds identically (composite.cu)
         rec[3 * i + 0] = make_float4(px, py, -0.5f * i00, -0.5f * i01);
         // the blend loop evaluates alpha = op2 * exp(power) as exp2(power*log2e + log2(op2)): one FFMA + MUFU.EX2
