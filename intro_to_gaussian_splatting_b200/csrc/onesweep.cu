@@ -31,9 +31,6 @@ constexpr int kHistItems = 16;
 constexpr int kSortTile = kThreads * kHistItems;  // keys per histogram chunk
 
 constexpr uint32_t kFlagShift = 30;
-constexpr uint32_t kFlagAggregate = 1u << kFlagShift;
-constexpr uint32_t kFlagPrefix = 2u << kFlagShift;
-constexpr uint32_t kValueMask = (1u << kFlagShift) - 1u;
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
   uint32_t v;
