@@ -30,7 +30,6 @@ constexpr int kLookBatch = 8;   // look-back loads in flight per lane
 constexpr int kHistItems = 16;
 constexpr int kSortTile = kThreads * kHistItems;  // keys per histogram chunk
 
-constexpr uint32_t kFlagShift = 30;
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
   uint32_t v;
