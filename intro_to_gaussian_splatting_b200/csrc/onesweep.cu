@@ -25,6 +25,9 @@ namespace gsb {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef GSB_RANK_GROUP
+#define GSB_RANK_GROUP 8
+#endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kLookBatch = 8;   // look-back loads in flight per lane
 constexpr int kHistItems = 16;
@@ -191,27 +194,32 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     }
   }
 
-  // 3. stable ranks inside the warp: all ballot matches first (independent), then the running counts (leaders
-  //    only, in item order), then all broadcasts.
-  unsigned peers[kItems];
-  uint32_t pos[kItems];
-  const unsigned lt_mask = (1u << lane) - 1u;
-#pragma unroll
-  for (int i = 0; i < kItems; ++i) peers[i] = match_digit(digit_fast(key[i], shift, mask), bits);
+  // 3. stable ranks inside the warp, in groups of kRankGroup items: the group's ballot matches first
+  //    (independent), then its running counts (leaders only, in item order), then its broadcasts -- enough ILP
+  //    to cover the ATOMS / SHFL latencies while only kRankGroup peer masks are live at a time.
   // Running per-digit count of this warp, kept by the group leaders (one leader per digit and item) with a
   // shared-memory atomic that returns the count before this item.  (A plain load + store by the leader is what
   // the arithmetic needs, but a different lane may lead the same digit in the next item: racecheck rightly flags
   // that, and ordering it with a __syncwarp() per item measured 6-8 us per frame slower than the atomic.)
+  constexpr int kRankGroup = GSB_RANK_GROUP < kItems ? GSB_RANK_GROUP : kItems;
+  uint32_t pos[kItems];
+  const unsigned lt_mask = (1u << lane) - 1u;
   uint32_t* wcnt = s_cnt[warp];
 #pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    pos[i] = 0;
-    if ((peers[i] & lt_mask) == 0u)  // lowest lane of its peer group == the leader
-      pos[i] = atomicAdd(&wcnt[digit_fast(key[i], shift, mask)], (uint32_t)__popc(peers[i]));
-  }
+  for (int g = 0; g < kItems; g += kRankGroup) {
+    unsigned peers[kRankGroup];
 #pragma unroll
-  for (int i = 0; i < kItems; ++i)
-    pos[i] = __shfl_sync(0xffffffffu, pos[i], __ffs(peers[i]) - 1) + (uint32_t)__popc(peers[i] & lt_mask);
+    for (int i = 0; i < kRankGroup; ++i) peers[i] = match_digit(digit_fast(key[g + i], shift, mask), bits);
+#pragma unroll
+    for (int i = 0; i < kRankGroup; ++i) {
+      pos[g + i] = 0;
+      if ((peers[i] & lt_mask) == 0u)  // lowest lane of its peer group == the leader
+        pos[g + i] = atomicAdd(&wcnt[digit_fast(key[g + i], shift, mask)], (uint32_t)__popc(peers[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < kRankGroup; ++i)
+      pos[g + i] = __shfl_sync(0xffffffffu, pos[g + i], __ffs(peers[i]) - 1) + (uint32_t)__popc(peers[i] & lt_mask);
+  }
   __syncthreads();
 
   // 4a. thread d owns digit d: scan the warp counters, publish the tile's aggregate as early as possible
