@@ -1,8 +1,9 @@
 """GPU parity of gsb_render_backward against oracle/backward_oracle.py, the float64
 autograd restatement of the reference's forward (its projection half is pinned to the reference's own autograd,
 tests/test_backward_oracle.py).  Tolerance (floating point, stated here): every gradient array within
-2e-3 of the oracle in norm, and element-wise within 1e-2*|ref| + 1e-3*max|ref| -- the CUDA side is fp32 with
-ex2.approx and float atomics, the oracle float64."""
+2e-4 of the oracle in norm, and element-wise within 1e-3*|ref| + 1e-4*max|ref| -- the CUDA side is fp32 with
+ex2.approx and float atomics, the oracle float64.  Measured on B200: norm errors 8e-7 .. 2e-5, element-wise at
+most a third of the band.  (The full-size property test and smoke() keep their own, looser bounds.)"""
 
 import numpy as np
 import pytest
@@ -44,8 +45,8 @@ def _close(got, ref, name):
     assert np.isfinite(got).all(), name
     scale = np.abs(ref).max()
     err = np.abs(got - ref)
-    assert (err <= 1e-2 * np.abs(ref) + 1e-3 * scale + 1e-9).all(), (name, float(err.max()), float(scale))
-    assert np.linalg.norm(got - ref) <= 2e-3 * np.linalg.norm(ref) + 1e-9, name
+    assert (err <= 1e-3 * np.abs(ref) + 1e-4 * scale + 1e-9).all(), (name, float(err.max()), float(scale))
+    assert np.linalg.norm(got - ref) <= 2e-4 * np.linalg.norm(ref) + 1e-9, name
 
 
 @pytest.mark.parametrize("spec,full_cover", [("tiny", 1), (DENSE, 1), (DENSE, 0), (WIDE, 1), (THICK, 1), ("small", 1)],
