@@ -34,6 +34,41 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.GsbFrameInfo) == 3 * 8 + 6 * 4
 
 
+def test_struct_layouts_match_a_c_compiler(tmp_path):
+    """Compile include/gsb.h with the host C compiler and compare sizeof / offsetof of every field with the ctypes
+    mirrors (this package's and the oracle's): the header is the single source of truth of the ABI."""
+    import shutil
+    import subprocess
+
+    from oracle import oracle as orc
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"GsbCamera": (_lib.GsbCamera, orc.Camera), "GsbParams": (_lib.GsbParams, orc.Params),
+               "GsbFrameInfo": (_lib.GsbFrameInfo, None)}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "gsb.h"', "int main(void) {"]
+    for name, (ct, _) in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _t in ct._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, (ct, oc) in structs.items():
+        assert int(got[name]) == C.sizeof(ct), name
+        for field, _t in ct._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(ct, field).offset, (name, field)
+        if oc is not None:
+            assert C.sizeof(oc) == C.sizeof(ct)
+            assert [f for f, _ in oc._fields_] == [f for f, _ in ct._fields_], name
+            for field, _t in oc._fields_:
+                assert getattr(oc, field).offset == getattr(ct, field).offset, (name, field)
+
+
 def test_default_params_are_the_reference_literals():
     p = _lib.default_params()
     assert p.tile_size == 16
