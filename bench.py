@@ -223,6 +223,26 @@ def stage_bytes(info, n, width, height, split):
     return b
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host
+    images of the e2e leg are first-touched on the NUMA node behind the GPU's PCIe root (torchrun does not bind
+    ranks).  Returns the number of CPUs bound to, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -241,7 +261,9 @@ def run_ours(args):
         raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        numa = bind_to_gpu_numa_node(local)  # before any pinned allocation: the e2e images are copied to host memory
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
     spec = CONFIGS[args.config]
@@ -441,7 +463,7 @@ def run_ours(args):
                    "value_with_flush_inside_timed_region": round(K * world / (ms_flush_max * 1e-3), 1),
                    "frame_latency_ms_serial": round(frame_latency_ms, 4),
                    "mean_in_view": round(mean_m), "mean_tile_instances": round(mean_k),
-                   "gaussian_broadcast_s": round(bcast_s, 4)},
+                   "gaussian_broadcast_s": round(bcast_s, 4), "cpus_bound_per_rank": numa},
         "e2e": {"value": K * world / (ms_e2e_max * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_max / K,
                 "h2d_bytes_per_step": C.sizeof(_lib.GsbCamera) + C.sizeof(_lib.GsbParams),
                 "d2h_bytes_per_step": H * Wd * 3 * 4 + 8,
