@@ -37,9 +37,10 @@ def fit(gaussians, cameras: Sequence[GsbCamera], targets: Sequence[torch.Tensor]
     Gaussians): at step s rank r differentiates view shard.view_of_step(s) -- R different views per step -- and the
     gradients are averaged with one packed all-reduce, so all ranks apply the same update; the returned losses
     are this rank's."""
-    rast = rasterizer or Rasterizer()
-    dev = rast.device
     rates = {"points": 1.6e-4, "scales": 5e-3, "quaternions": 1e-3, "colors": 2.5e-3, "opacity": 5e-2}
+    unknown = set(lr or {}) - set(ATTRIBUTES)
+    if unknown:
+        raise ValueError(f"learning rates for unknown attributes {sorted(unknown)}")
     rates.update(lr or {})
     trainable = set(trainable)
     unknown = trainable - set(ATTRIBUTES)
@@ -47,6 +48,11 @@ def fit(gaussians, cameras: Sequence[GsbCamera], targets: Sequence[torch.Tensor]
         raise ValueError(f"unknown attributes {sorted(unknown)}")
     if len(cameras) == 0 or len(cameras) != len(targets):
         raise ValueError("fit: need one target image per camera")
+    for cam, tgt in zip(cameras, targets):
+        if tuple(tgt.shape) != (cam.height, cam.width, 3):
+            raise ValueError(f"fit: target of shape {tuple(tgt.shape)} for a {cam.height}x{cam.width} camera")
+    rast = rasterizer or Rasterizer()  # raises without a CUDA device: there is no CPU path
+    dev = rast.device
     leaves = {}
     for k in ATTRIBUTES:
         t = getattr(gaussians, k).detach().to(dev, torch.float32).clone()

@@ -76,3 +76,27 @@ def test_synth_is_deterministic_and_matches_its_spec():
     c1 = make_scene("cfg1", n_override=10)
     assert torch.all(c1.scales == 0.01) and torch.all(c1.quats[:, 0] == 1) and len(c1.views) == 1
     assert len(make_scene("cfg4", n_override=4).views) == 256
+
+
+def test_fit_validates_its_arguments_before_touching_the_gpu():
+    """train.fit argument errors are ValueErrors raised before a rasterizer (GPU) is needed."""
+    from types import SimpleNamespace
+
+    import pytest
+    import torch
+
+    from intro_to_gaussian_splatting_b200 import _lib, fit
+
+    cam = _lib.GsbCamera()
+    cam.width, cam.height = 32, 16
+    gs = SimpleNamespace(points=torch.zeros(1, 3), scales=torch.ones(1, 3), quaternions=torch.ones(1, 4),
+                         colors=torch.zeros(1, 3), opacity=torch.zeros(1, 1))
+    ok = torch.zeros(16, 32, 3)
+    with pytest.raises(ValueError, match="one target"):
+        fit(gs, [cam], [], steps=1)
+    with pytest.raises(ValueError, match="unknown attributes"):
+        fit(gs, [cam], [ok], steps=1, trainable=("points", "colour"))
+    with pytest.raises(ValueError, match="learning rates"):
+        fit(gs, [cam], [ok], steps=1, lr={"colour": 1.0})
+    with pytest.raises(ValueError, match="target of shape"):
+        fit(gs, [cam], [torch.zeros(32, 16, 3)], steps=1)
