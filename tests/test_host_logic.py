@@ -100,3 +100,33 @@ def test_fit_validates_its_arguments_before_touching_the_gpu():
         fit(gs, [cam], [ok], steps=1, lr={"colour": 1.0})
     with pytest.raises(ValueError, match="target of shape"):
         fit(gs, [cam], [torch.zeros(32, 16, 3)], steps=1)
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (outputs of bench.py on the B200 pool) carry every key of the bench
+    contract; the reference arm's line carries its own."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = json.load(open(os.path.join(root, "profiles", "r1_bench_cfg3_1gpu.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in ours, k
+    assert "workload" in ours["config"] and "model" not in ours["config"]
+    assert ours["n_gpus"] == 1 and ours["scaling"] == "weak" and ours["higher_is_better"] is True
+    assert ours["vs_baseline"] is None and ours["data"] == "synthetic" and ours["warmup"] >= 3
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in ours["e2e"], k
+    assert ours["e2e"]["d2h_bytes_per_step"] >= 1920 * 1080 * 3 * 4 and ours["e2e"]["value"] != ours["value"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in ours["roofline"], k
+    assert ours["roofline"]["bound"] in ("hbm", "tensor")
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in ours["cpu_baseline"], k
+    assert ours["cpu_baseline"]["kind"] in ("port", "reference")
+    assert ours["gpu_launches"] > 0 and not ours["clocks"]["reasons"]
+    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference_arm.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
+    assert ref["cpu_baseline"]["value"] == ref["value"]
