@@ -161,6 +161,22 @@ struct SortSmem {
   uint32_t tile;
 };
 
+// Opt-in phase clocks (-DGSB_PHASE_CLOCKS, tools/phase_clocks.py): thread 0 of every tile of the keys-only passes
+// adds the cycles between consecutive marks to g_phase[mark]; g_phase[15] counts tiles.  Off in the shipped library.
+#ifdef GSB_PHASE_CLOCKS
+__device__ unsigned long long g_phase[16];
+#define GSB_PHASE(k)                                                        \
+  do {                                                                      \
+    if (kMode == kKeysOnly && threadIdx.x == 0) {                           \
+      const long long _t = clock64();                                       \
+      atomicAdd(&g_phase[k], (unsigned long long)(_t - _t_prev));           \
+      _t_prev = _t;                                                         \
+    }                                                                       \
+  } while (0)
+#else
+#define GSB_PHASE(k) do { } while (0)
+#endif
+
 // kFull: the tile holds kThreads*kItems keys (every tile but the last) -> straight-line code, no bounds checks
 template <typename KeyT, int kItems, int kMode, bool kFull, typename W>
 __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const KeyT* __restrict__ keys_in,
@@ -180,6 +196,10 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
   constexpr bool full = kFull;
   const KeyT kPad = ~(KeyT)0;
 
+#ifdef GSB_PHASE_CLOCKS
+  long long _t_prev = clock64();
+  if (kMode == kKeysOnly && threadIdx.x == 0) atomicAdd(&g_phase[15], 1ull);
+#endif
   // 2. warp-striped coalesced loads
   KeyT key[kItems];
   const int64_t wbase = base + (int64_t)warp * (32 * kItems) + lane;
@@ -220,7 +240,9 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     for (int i = 0; i < kRankGroup; ++i)
       pos[g + i] = __shfl_sync(0xffffffffu, pos[g + i], __ffs(peers[i]) - 1) + (uint32_t)__popc(peers[i] & lt_mask);
   }
+  GSB_PHASE(0);  // load + rank (thread 0's warp)
   __syncthreads();
+  GSB_PHASE(1);  // wait for the slowest warp
 
   // 4a. thread d owns digit d: scan the warp counters, publish the tile's aggregate as early as possible
   uint32_t real, tile_start, bin_base;
@@ -266,6 +288,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     for (int w = 0; w < kWarps; ++w) s_cnt[w][d] += tile_start;
   }
   __syncthreads();
+  GSB_PHASE(2);  // digit scan + publish
 
   // 5a. keys -> smem in locally sorted order (gives earlier tiles time to publish before the look-back)
 #pragma unroll
@@ -274,6 +297,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     exch.keys[pos[i]] = key[i];
   }
 
+  GSB_PHASE(3);  // scatter to shared memory
   // 4b. decoupled look-back for this thread's digit.  Predecessor words are fetched in BATCHES of
   //     independent loads (2 first -- in steady state the nearest tiles already hold an inclusive prefix --
   //     then 8 at a time): at the start of a pass several hundred tiles are in flight with only their
@@ -318,7 +342,9 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
     }
     s_gofs[tid] = bin_base + excl - tile_start;  // global index = s_gofs[d] + local position (mod 2^32)
   }
+  GSB_PHASE(4);  // look-back of digit 0
   __syncthreads();
+  GSB_PHASE(5);  // wait for the slowest digit
 
   // 5b. keys -> global: consecutive threads write consecutive addresses inside each digit run
   uint32_t dst[kItems];
@@ -355,6 +381,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
       if (full || j < valid) vals_out[dst[i]] = exch.vals[j];
     }
   }
+  GSB_PHASE(6);  // write
 }
 
 #ifndef GSB_SORT_MINBLOCKS16
@@ -386,6 +413,15 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 
 }  // namespace
 
+#ifdef GSB_PHASE_CLOCKS
+// debug build only (not declared in include/gsb.h): copy out and reset the phase clocks
+extern "C" int gsb_debug_phase_clocks(unsigned long long* out) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+  return (int)e;
+}
+#endif
 static int g_sort_items = 16;  // keys per thread of the onesweep tile (8 or 16); tuning knob, see gsb_api.cu
 void set_sort_items(int items) { g_sort_items = (items == 8) ? 8 : 16; }
 static int g_force_wide = 0;   // test knob: use the 64-bit look-back words regardless of the key count
