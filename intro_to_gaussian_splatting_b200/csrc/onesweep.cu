@@ -309,6 +309,9 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
       const W* col = status + tid;  // status is [tile][256]
       int64_t t = (int64_t)tile - 1;
       bool found = false;
+#ifdef GSB_PHASE_CLOCKS
+      unsigned long long n_words = 0, n_spins = 0;
+#endif
       {
         W v[2];
 #pragma unroll
@@ -317,7 +320,15 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
         for (int k = 0; k < 2; ++k) {
           if (found) break;
           W x = v[k];
-          while ((x >> SW::kShift) == 0) x = SW::ld(col + (size_t)(t - k) * kRadix);
+          while ((x >> SW::kShift) == 0) {
+#ifdef GSB_PHASE_CLOCKS
+            ++n_spins;
+#endif
+            x = SW::ld(col + (size_t)(t - k) * kRadix);
+          }
+#ifdef GSB_PHASE_CLOCKS
+          ++n_words;
+#endif
           excl += (uint32_t)(x & kWMask);
           found = (x >> SW::kShift) == 2u;
         }
@@ -332,13 +343,24 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
         for (int k = 0; k < kLookBatch; ++k) {
           if (found) break;
           W x = v[k];
-          while ((x >> SW::kShift) == 0) x = SW::ld(col + (size_t)(t - k) * kRadix);
+          while ((x >> SW::kShift) == 0) {
+#ifdef GSB_PHASE_CLOCKS
+            ++n_spins;
+#endif
+            x = SW::ld(col + (size_t)(t - k) * kRadix);
+          }
+#ifdef GSB_PHASE_CLOCKS
+          ++n_words;
+#endif
           excl += (uint32_t)(x & kWMask);
           found = (x >> SW::kShift) == 2u;
         }
         t -= kLookBatch;
       }
       SW::st(st, kWPre | (((W)excl + (W)real) & kWMask));
+#ifdef GSB_PHASE_CLOCKS
+      if (kMode == kKeysOnly && threadIdx.x == 0) { atomicAdd(&g_phase[8], n_words); atomicAdd(&g_phase[9], n_spins); }
+#endif
     }
     s_gofs[tid] = bin_base + excl - tile_start;  // global index = s_gofs[d] + local position (mod 2^32)
   }

@@ -61,5 +61,5 @@ for f in range(6):
     n = out[15]
     if f >= 3 and n:
         print(f"frame {f}: {n} tiles: " + "; ".join(f"{nm} {out[k] / n:.0f}" for k, nm in enumerate(names))
-              + f"; total {sum(out[k] for k in range(7)) / n:.0f} cycles", flush=True)
+              + f"; total {sum(out[k] for k in range(7)) / n:.0f} cycles; look-back words per walk {out[8] / n:.1f}, re-reads while waiting {out[9] / n:.1f}", flush=True)
 shutil.rmtree(work, ignore_errors=True)
