@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GSB_API_VERSION 1
+#define GSB_API_VERSION 2
 
 /* ---- status codes (negative: library; positive: cudaError_t) ---- */
 #define GSB_OK 0
@@ -53,11 +53,11 @@ extern "C" {
 #define GSB_SEM_REF_CU 1  /* splat/c/render.cu:21-87: informational */
 
 /* ---- sort organisation; both give bit-identical sorted (key,payload) arrays ---- */
-#define GSB_SORT_AUTO 0
-#define GSB_SORT_FULL 1  /* expand in index order, 64-bit LSD onesweep over all K keys */
-#define GSB_SORT_SPLIT 2 /* depth digits sorted per Gaussian (M items) before expansion, tile digits after */
-#define GSB_SORT_BINNED 3 /* per-Gaussian depth sort, instances dropped into exact per-tile segments, each segment
-                            sorted by depth rank in shared memory */
+#define GSB_SORT_AUTO 0  /* = SPLIT */
+#define GSB_SORT_FULL 1  /* expand in index order, 64-bit LSD onesweep over all K (tile<<32 | depth) keys */
+#define GSB_SORT_SPLIT 2 /* depth digits sorted per Gaussian (N items) BEFORE the expansion; the expansion then runs
+                            in two levels: one key per SUPER-TILE (8x4 tiles at 1080p) of the rect, one radix pass
+                            over the super-tile ids, and a stable per-tile compaction of each super-tile's list */
 
 /* Per-view camera constants, exactly the tensors GaussianImage holds (splat/image.py:19-70).
  * Matrices are row-major with the reference's row-vector convention: row = [x y z 1] @ M.
@@ -90,17 +90,24 @@ typedef struct GsbParams {
                               gsb_join_host_copies(ctx, stream) + a synchronisation of that stream */
   int32_t save_for_backward; /* 1: gsb_render also keeps, per pixel, the number of blended Gaussians and the final
                                 transmittance, so that gsb_render_backward can follow (REF_CPU semantics only) */
+  float cull_alpha;    /* REF_CPU compositing: a warp skips a Gaussian when a conservative upper bound of its alpha
+                          over the warp's 16x8 pixels is below this value.  The reference evaluates every Gaussian
+                          of a tile at every pixel (no per-pixel bbox test, splat/gaussian_scene.py:209-226), most of
+                          them with alpha that fp32 cannot see.  0: skip only alpha that is EXACTLY zero in fp32
+                          (frames bit-identical to no skipping); t > 0: a skipped step would have changed a pixel by
+                          < t, a frame differs by < t x list length; < 0: never skip.  Default 2^-30. */
 } GsbParams;
 
 /* Stage indices for gsb_stage_times (CUDA events on the caller's stream) */
 #define GSB_STAGE_PROJECT 0
 #define GSB_STAGE_DEPTH_SORT 1 /* per-Gaussian depth sort (SPLIT / BINNED) */
 #define GSB_STAGE_SCAN 2       /* prefix sum of the tile counts */
-#define GSB_STAGE_EMIT 3       /* key emission (includes the wait for the M/K mailbox, normally zero) */
-#define GSB_STAGE_SORT 4       /* radix passes over the K keys (BINNED: per-tile sort) */
-#define GSB_STAGE_RANGES 5     /* tile statistics; runs on the auxiliary stream in FULL/SPLIT and reads 0 there */
+#define GSB_STAGE_EMIT 3       /* key emission (FULL: one key per tile instance; SPLIT: one per super-tile instance) */
+#define GSB_STAGE_SORT 4       /* radix passes over those keys */
+#define GSB_STAGE_RANGES 5     /* tile statistics; runs on the auxiliary stream and reads 0 */
 #define GSB_STAGE_COMPOSITE 6
-#define GSB_NUM_STAGES 7
+#define GSB_STAGE_EXPAND 7     /* SPLIT: per-tile lists from the super-tile lists */
+#define GSB_NUM_STAGES 8
 
 /* Per-frame counts (valid after a render / preprocess call has completed on its stream). */
 typedef struct GsbFrameInfo {
@@ -111,7 +118,10 @@ typedef struct GsbFrameInfo {
   int32_t sort_passes; /* onesweep passes executed over the K keys */
   int32_t depth_passes;/* onesweep passes executed over the M depth keys (split mode) */
   int32_t kernel_launches; /* kernels launched by the last gsb_render */
-  int32_t key_bits;    /* width of the tile-sort keys of the last frame: 32 or 64 (0: no K-sized sort, BINNED) */
+  int32_t key_bits;    /* width of the keys of the last frame's tile-level radix passes: 32 or 64 */
+  int64_t k_sorted;    /* keys those passes moved: K (FULL) or the number of super-tile instances (SPLIT) */
+  int64_t frame_id;    /* increases with every frame this context renders; gsb_render_backward checks it */
+  int32_t super_w, super_h; /* SPLIT: tiles per super-tile (1 x 1: single-level binning) */
 } GsbFrameInfo;
 
 typedef struct GsbContext GsbContext;
@@ -134,9 +144,12 @@ int gsb_upload(GsbContext* ctx, int64_t n, const float* xyz, const float* scales
 /* The forward render: projection -> tile binning -> radix sort -> tile ranges -> compositing.
  * Replaces GaussianScene.preprocess + ext.render_image (splat/gaussian_scene.py:263-285).
  * out_image: (H,W,3) fp32, image[y][x][c] like render.cu:83-85; dev-or-host.  `cam`/`params`
- * are host structs, copied before return.  The call returns once the data-dependent tile-instance
- * count K has reached the host (mailbox in mapped pinned memory; the stream is NOT drained) and the
- * rest of the frame is queued. */
+ * are host structs, copied before return.  The WHOLE frame is queued before the host looks at anything
+ * data-dependent: grids and buffers are sized from the context's capacities, the device decides whether
+ * the frame's counts fit, and the call returns once those counts (M, K) have reached the host through a
+ * mailbox in mapped pinned memory -- the stream is never drained and never waits for the host.  Only when
+ * a count outgrew its buffer (first frames, or a view with many more tile instances) does the host grow
+ * the buffer and queue the tail of the frame again. */
 int gsb_render(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, float* out_image,
                void* stream);
 
@@ -147,14 +160,16 @@ int gsb_join_host_copies(GsbContext* ctx, void* stream);
 
 /* Backward pass of the LAST gsb_render of this context (the reference announces training,
  * README.md:3, and marks splat/gaussians.py:19-21 requires_grad, but never wrote it).  That render must have been
- * made with params.save_for_backward = 1 and the same camera / params (compared bytewise; GSB_E_NO_SAVED otherwise).
+ * made with params.save_for_backward = 1 and the same camera / params (compared bytewise), and nothing else may
+ * have been rendered, preprocessed or uploaded on the context since (GSB_E_NO_SAVED otherwise).  frame_id: the
+ * GsbFrameInfo.frame_id of the render being differentiated, or 0 for "whatever the last saved frame is".
  * grad_image: dL/d image, (H,W,3) fp32, device or host.  Outputs (device or host, any may be NULL), in the
  * reference's attribute layouts: grad_points (N,3), grad_scales (N,3), grad_quats (N,4), grad_colors (N,3),
  * grad_opacity (N,1) -- the gradient wrt the opacity LOGIT.  Tile membership, depth order, early termination and
  * the clamps are treated as piecewise constant.  Sums use float atomics: results are reproducible to rounding,
  * not bit for bit. */
-int gsb_render_backward(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, const float* grad_image,
-                        float* grad_points, float* grad_scales, float* grad_quats, float* grad_colors,
+int gsb_render_backward(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, int64_t frame_id,
+                        const float* grad_image, float* grad_points, float* grad_scales, float* grad_quats, float* grad_colors,
                         float* grad_opacity, void* stream);
 
 /* Same frame, egress variants: (W,H,3) layout of the reference CPU

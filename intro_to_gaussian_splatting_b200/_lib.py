@@ -18,9 +18,9 @@ GSB_SEM_REF_CU = 1
 GSB_SORT_AUTO = 0
 GSB_SORT_FULL = 1
 GSB_SORT_SPLIT = 2
-GSB_SORT_BINNED = 3
-GSB_NUM_STAGES = 7
-STAGE_NAMES = ("project", "depth_sort", "scan", "emit", "sort", "ranges", "composite")
+GSB_API_VERSION = 2
+GSB_NUM_STAGES = 8
+STAGE_NAMES = ("project", "depth_sort", "scan", "emit", "sort", "ranges", "composite", "expand")
 
 # every symbol include/gsb.h declares (tests check that the .so exports exactly these)
 EXPORTED_SYMBOLS = (
@@ -60,6 +60,7 @@ class GsbParams(C.Structure):
         ("collect_stage_times", C.c_int32),
         ("async_host_copy", C.c_int32),
         ("save_for_backward", C.c_int32),
+        ("cull_alpha", C.c_float),
     ]
 
 
@@ -74,6 +75,10 @@ class GsbFrameInfo(C.Structure):
         ("depth_passes", C.c_int32),
         ("kernel_launches", C.c_int32),
         ("key_bits", C.c_int32),
+        ("k_sorted", C.c_int64),
+        ("frame_id", C.c_int64),
+        ("super_w", C.c_int32),
+        ("super_h", C.c_int32),
     ]
 
 
@@ -114,7 +119,7 @@ def load() -> C.CDLL:
     lib.gsb_stage_times.argtypes = [vp, C.POINTER(C.c_float * GSB_NUM_STAGES)]
     lib.gsb_sort_pairs_u64.argtypes = [vp, i64, vp, vp, vp, vp, i32, i32, vp]
     lib.gsb_join_host_copies.argtypes = [vp, vp]
-    lib.gsb_render_backward.argtypes = [vp, C.POINTER(GsbCamera), C.POINTER(GsbParams)] + [vp] * 7
+    lib.gsb_render_backward.argtypes = [vp, C.POINTER(GsbCamera), C.POINTER(GsbParams), i64] + [vp] * 7
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("gsb_error_string", "gsb_default_params", "gsb_destroy"):

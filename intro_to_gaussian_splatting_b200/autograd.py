@@ -23,13 +23,17 @@ class _RenderFunction(torch.autograd.Function):
                 opacity):
         rast.upload(points, scales, quaternions, colors, opacity)
         image = rast.render(cam, params)
+        # the saved state lives in the rasterizer's per-frame scratch: remember WHICH frame this graph belongs to, so
+        # that a backward after any other render / preprocess / upload on the rasterizer fails instead of reading
+        # another frame's lists
+        ctx.frame_id = rast.last_frame_id
         ctx.rast, ctx.cam, ctx.params = rast, cam, params
         ctx.opacity_shape = tuple(opacity.shape)
         return image
 
     @staticmethod
     def backward(ctx, grad_image):
-        g = ctx.rast.render_backward(ctx.cam, ctx.params, grad_image)
+        g = ctx.rast.render_backward(ctx.cam, ctx.params, grad_image, frame_id=ctx.frame_id)
         need = ctx.needs_input_grad[3:]
         outs = [g["points"], g["scales"], g["quaternions"], g["colors"], g["opacity"].reshape(ctx.opacity_shape)]
         return (None, None, None) + tuple(o if n else None for o, n in zip(outs, need))

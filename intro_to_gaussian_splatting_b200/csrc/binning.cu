@@ -7,8 +7,16 @@
 // (SURVEY.md Appendix A.8).  The per-tile [start,end) ranges of the sorted array are known before any key exists:
 // tile_stats_kernel derives them from the 2-D difference grid of tile rects written by the projection kernel.
 //
-// Roofline: HBM.  scan: 8 B read + 4 B written per Gaussian.  emit: 8-12 B written per key (+ 24 B per Gaussian
-// read).  tile stats: 4 B per grid cell read, 8 B per tile written.
+//
+// SPLIT mode does the expansion in two levels: the Gaussians, already in depth order, are
+// first expanded into SUPER-TILE instances (a super-tile is 2^lw x 2^lh tiles, chosen so that the frame has at most
+// 256 of them: 8x4 tiles at 1080p), those few keys take ONE stable radix pass over the super-tile id, and
+// expand_kernel then derives every tile's list from its super-tile's list with a stable warp-wide compaction --
+// the per-tile start offsets are known up front from tile_stats_kernel, so no key is ever written per tile
+// instance and nothing K-sized is sorted.
+//
+// Roofline: HBM.  scan: 12 B read + 4 B written per Gaussian.  emit: 4-12 B written per key (+ 24 B per Gaussian
+// read).  tile stats: 4 B per grid cell read, 8 B per tile written.  expand: 4 B written per tile instance.
 #include "gsb_internal.cuh"
 
 namespace gsb {
@@ -58,8 +66,18 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 size_t scan_status_words(int64_t n) { return 2 * ((size_t)((n + kScanTile - 1) / kScanTile) + 2); }
 
+// kFromRect: the scanned value is the number of SUPER-TILES the row's rect touches (rect.y < rect.x marks "no
+// tiles"), computed on the fly; rows at emission positions >= *v_limit (the Gaussians without tiles, which the depth
+// sort leaves at the end) are not even read.
+__device__ __forceinline__ uint32_t coarse_count(ushort4 r, int lw, int lh) {
+  if (r.y < r.x) return 0u;
+  return (uint32_t)((r.y >> lw) - (r.x >> lw) + 1) * (uint32_t)((r.w >> lh) - (r.z >> lh) + 1);
+}
+
+template <bool kFromRect>
 __global__ void __launch_bounds__(kScanThreads)
-scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ perm, int64_t n,
+scan_kernel(const uint32_t* __restrict__ count, const ushort4* __restrict__ rect, int lw, int lh,
+            const uint32_t* __restrict__ perm, int64_t n, const uint32_t* __restrict__ v_limit,
             uint32_t* __restrict__ offsets, uint32_t* status) {
   constexpr uint64_t kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
   __shared__ uint32_t s_block, s_excl;
@@ -69,6 +87,11 @@ scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
   __syncthreads();
   const uint32_t b = s_block;
   uint64_t* st = reinterpret_cast<uint64_t*>(status) + 1;
+  if (v_limit) {  // rows past the limit carry nothing: a CTA that starts there has no successor that needs it
+    const int64_t lim = (int64_t)*v_limit;
+    n = lim < n ? lim : n;
+    if ((int64_t)b * kScanTile >= n) return;
+  }
   const int64_t base = (int64_t)b * kScanTile + (int64_t)tid * kScanItems;
   uint32_t v[kScanItems];
   uint32_t local = 0;
@@ -76,7 +99,10 @@ scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
   for (int k = 0; k < kScanItems; ++k) {
     const int64_t i = base + k;
     uint32_t c = 0;
-    if (i < n) c = perm ? count[perm[i]] : count[i];
+    if (i < n) {
+      const int64_t g = perm ? (int64_t)perm[i] : i;
+      c = kFromRect ? coarse_count(rect[g], lw, lh) : count[g];
+    }
     v[k] = local;  // exclusive within the thread
     local += c;
   }
@@ -131,7 +157,16 @@ scan_kernel(const uint32_t* __restrict__ count, const uint32_t* __restrict__ per
 int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* status,
                 cudaStream_t st) {
   if (n == 0) return 0;
-  scan_kernel<<<(unsigned)((n + kScanTile - 1) / kScanTile), kScanThreads, 0, st>>>(count, perm, n, offsets, status);
+  scan_kernel<false><<<(unsigned)((n + kScanTile - 1) / kScanTile), kScanThreads, 0, st>>>(
+      count, nullptr, 0, 0, perm, n, nullptr, offsets, status);
+  return (int)cudaGetLastError();
+}
+
+int launch_scan_coarse(const ushort4* rect, SuperGeom sg, const uint32_t* perm, int64_t n, const uint32_t* v_limit,
+                       uint32_t* offsets, uint32_t* status, cudaStream_t st) {
+  if (n == 0) return 0;
+  scan_kernel<true><<<(unsigned)((n + kScanTile - 1) / kScanTile), kScanThreads, 0, st>>>(
+      nullptr, rect, sg.lw, sg.lh, perm, n, v_limit, offsets, status);
   return (int)cudaGetLastError();
 }
 
@@ -143,10 +178,15 @@ constexpr int kEmitChunk = GSB_EMIT_CHUNK;   // output slots per block
 constexpr int kEmitWindow = 512;   // Gaussians staged per window
 constexpr uint32_t kEmitRun = 16;  // consecutive output slots per thread and search
 
+// The SPLIT kinds emit one key per SUPER-TILE of the rect (rect >> (lw, lh), tiles_x = super-tiles per row); with
+// lw = lh = 0 that is one key per tile.  The grid is sized from the CAPACITY of the key buffer, not from the key
+// count (which only the device knows when the kernel is queued): blocks past *total leave at once, and nothing
+// runs when *abort is set (the count exceeded the capacity; the host re-queues the frame's tail after growing).
 template <int kKind>
 __global__ void __launch_bounds__(kEmitThreads)
 emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
-            int64_t n, const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x,
+            int64_t n, const uint32_t* __restrict__ v_limit, const uint32_t* __restrict__ abort,
+            const uint32_t* __restrict__ depth_key, const ushort4* __restrict__ rect, int tiles_x, int lw, int lh,
             int rank_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
   constexpr bool kCombined = kKind != kEmitFull;
   __shared__ uint32_t s_off[kEmitWindow + 1];
@@ -154,9 +194,14 @@ emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ p
   __shared__ uint32_t s_low[kEmitWindow];  // low key word: depth bits (FULL), Gaussian index or emission position
   __shared__ ushort4 s_rect[kEmitWindow];
   __shared__ int64_t s_bound[2];
+  if (abort && *abort) return;
   const uint32_t k_total = *total;
   const uint32_t c0 = blockIdx.x * (uint32_t)kEmitChunk;
   if (c0 >= k_total) return;
+  if (v_limit) {  // rows past the limit touch no tile and their offsets were never written
+    const int64_t lim = (int64_t)*v_limit;
+    n = lim < n ? lim : n;
+  }
   const uint32_t c1 = (k_total - c0 > (uint32_t)kEmitChunk) ? c0 + kEmitChunk : k_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < 2) {
@@ -186,7 +231,8 @@ emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ p
       s_off[j] = offsets[i];
       s_gid[j] = g;
       s_low[j] = kKind == kEmitSplit32 ? (uint32_t)i : (kKind == kEmitSplit64 ? g : depth_key[g]);
-      s_rect[j] = rect[g];
+      const ushort4 rf = rect[g];
+      s_rect[j] = kCombined ? make_ushort4(rf.x >> lw, rf.y >> lw, rf.z >> lh, rf.w >> lh) : rf;
     }
     if (threadIdx.x == 0) s_off[cntw] = (w0 + cntw < n) ? offsets[w0 + cntw] : k_total;
     __syncthreads();
@@ -276,19 +322,28 @@ emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ p
 }
 
 int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n, int64_t k,
-                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, int rank_bits,
-                uint64_t* keys, uint32_t* payload, cudaStream_t st) {
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, uint64_t* keys, uint32_t* payload,
+                cudaStream_t st) {
   if (n == 0 || k <= 0) return 0;
   unsigned blocks = (unsigned)((k + kEmitChunk - 1) / kEmitChunk);
-  if (combined && rank_bits > 0)
-    emit_kernel<kEmitSplit32><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x,
-                                                               rank_bits, keys, payload);
-  else if (combined)
-    emit_kernel<kEmitSplit64><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, 0,
-                                                               keys, payload);
+  emit_kernel<kEmitFull><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, nullptr, nullptr, depth_key, rect,
+                                                          tiles_x, 0, 0, 0, keys, payload);
+  return (int)cudaGetLastError();
+}
+
+int launch_emit_coarse(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
+                       const uint32_t* v_limit, const uint32_t* abort, int64_t capacity, const ushort4* rect,
+                       SuperGeom sg, int rank_bits, void* keys, cudaStream_t st) {
+  if (n == 0 || capacity <= 0) return 0;
+  unsigned blocks = (unsigned)((capacity + kEmitChunk - 1) / kEmitChunk);
+  if (rank_bits > 0)
+    emit_kernel<kEmitSplit32><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, v_limit, abort, nullptr, rect,
+                                                               sg.nx, sg.lw, sg.lh, rank_bits,
+                                                               reinterpret_cast<uint64_t*>(keys), nullptr);
   else
-    emit_kernel<kEmitFull><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, depth_key, rect, tiles_x, 0, keys,
-                                                            payload);
+    emit_kernel<kEmitSplit64><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, v_limit, abort, nullptr, rect,
+                                                               sg.nx, sg.lw, sg.lh, 0,
+                                                               reinterpret_cast<uint64_t*>(keys), nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -312,160 +367,81 @@ int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload,
 }
 
 // ------------------------------------------------------------------------------------------------
-// BINNED mode: per-tile lists without a global sort over the K instances.
+// expand: per-tile lists from per-super-tile lists (SPLIT mode, second level).
 //
-// The exact number of instances of every tile is known before a single key exists (tile_stats_kernel), so
-// every tile owns a fixed segment [start,end) of the payload array.  emit_binned_kernel drops each
-// (Gaussian, tile) instance into its tile's segment through a per-tile atomic cursor -- unordered -- and
-// tile_sort_kernel then sorts each segment BY DEPTH RANK in shared memory.  The depth rank (position of the
-// Gaussian in the stable depth sort of kernel 2) is unique per Gaussian and already encodes the tie order,
-// so sorting a segment by rank reproduces exactly the order the 64-bit key sort would give, with a 20-bit key
-// (N = 1 M) instead of 45 bits, on data that never leaves the SM.
+// After the one radix pass over the super-tile ids, cpay[ranges_s[s].x .. ranges_s[s].y) holds the Gaussians whose
+// rect touches super-tile s, in depth order.  Tile t of s needs exactly those of them whose rect covers t, in the
+// same order, at payload[ranges[t].x ..] -- a stable stream compaction, and the destination of every tile is known
+// before the first key exists (tile_stats_kernel).  One warp per tile: 32 list entries per step, one ballot, the
+// hits leave as one run of consecutive 4-byte stores.  The 16 warps of a CTA serve 16 tiles of the same super-tile
+// and share its list through shared memory (512 entries per window: index + rect gathered once per CTA,
+// prefetched one window ahead in registers).  No atomics, no look-back, no key: deterministic by construction.
+//
+// Work: tiles * (super-tile list length / 32) warp-steps of ~14 instructions -- a fraction of what a radix pass over
+// the K tile instances executes, and the only K-sized traffic is the 4 B per instance this kernel writes.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-invert_perm_kernel(const uint32_t* __restrict__ order, int64_t n, uint32_t* __restrict__ rank) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) rank[order[j]] = (uint32_t)j;
-}
+constexpr int kExpWarps = 16;
+constexpr int kExpThreads = kExpWarps * 32;
 
-int launch_invert_perm(const uint32_t* order, int64_t n, uint32_t* rank, cudaStream_t st) {
-  if (n == 0) return 0;
-  invert_perm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, n, rank);
-  return (int)cudaGetLastError();
-}
-
-// One warp looks after 32 consecutive Gaussians; those with a non-empty rect are expanded one after the
-// other by the WHOLE warp (32 tiles per step), so a Gaussian covering 2 000 tiles is spread over all lanes.
-__global__ void __launch_bounds__(256)
-emit_binned_kernel(int64_t n, const ushort4* __restrict__ rect, const uint32_t* __restrict__ count, int tiles_x,
-                   const uint2* __restrict__ ranges, uint32_t* __restrict__ cursor, uint32_t* __restrict__ payload) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  ushort4 r = make_ushort4(0, 0, 0, 0);
-  uint32_t cnt = 0;
-  if (i < n) { cnt = count[i]; if (cnt) r = rect[i]; }
-  unsigned todo = __ballot_sync(0xffffffffu, cnt != 0);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const uint32_t c = __shfl_sync(0xffffffffu, cnt, src);
-    const uint32_t x0 = __shfl_sync(0xffffffffu, (uint32_t)r.x, src), x1 = __shfl_sync(0xffffffffu, (uint32_t)r.y, src);
-    const uint32_t y0 = __shfl_sync(0xffffffffu, (uint32_t)r.z, src);
-    const uint32_t w = x1 - x0 + 1u;
-    const uint32_t g = (uint32_t)(i - lane + src);
-    for (uint32_t t = lane; t < c; t += 32) {
-      const uint32_t tile = (y0 + t / w) * (uint32_t)tiles_x + x0 + t % w;
-      const uint32_t slot = ranges[tile].x + atomicAdd(&cursor[tile], 1u);
-      payload[slot] = g;
-    }
-  }
-}
-
-int launch_emit_binned(int64_t n, const ushort4* rect, const uint32_t* count, int tiles_x, const uint2* ranges,
-                       uint32_t* cursor, uint32_t* payload, cudaStream_t st) {
-  if (n == 0) return 0;
-  emit_binned_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, rect, count, tiles_x, ranges, cursor, payload);
-  return (int)cudaGetLastError();
-}
-
-// Per-tile LSD radix sort of the segment by depth rank: 8-bit digits, ceil(rank_bits/8) passes, data in
-// shared memory (or, for segments longer than the shared-memory capacity, in the caller's global scratch --
-// the code is the same, only the pointers differ).  Each pass is stable: warp w owns a contiguous slice of
-// the segment and walks it 32 items at a time in order; in-warp ranks come from __match_any_sync, the warp's
-// running per-digit count lives in a counter row, and the rows are combined by an exclusive scan over
-// (digit, warp).  Input payload[start..end) holds Gaussian indices; output the same indices, depth-sorted.
-constexpr int kTsThreads = 256;
-constexpr int kTsWarps = kTsThreads / 32;
-constexpr int kTsBits = 8;
-constexpr int kTsBins = 1 << kTsBits;
-
-__global__ void __launch_bounds__(kTsThreads)
-tile_sort_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ order,
-                 uint32_t* __restrict__ payload, int rank_bits, uint32_t smem_items, uint32_t* __restrict__ scratch_a,
-                 uint32_t* __restrict__ scratch_b) {
-  extern __shared__ uint32_t s_dyn[];                 // [2][smem_items] ping-pong buffers
-  __shared__ uint32_t s_cnt[kTsWarps][kTsBins];  // per-warp digit counts -> exclusive offsets
-  __shared__ uint32_t s_part[kTsThreads];
-
-  const uint2 rg = ranges[blockIdx.x];
-  const uint32_t L = rg.y - rg.x;
-  if (L == 0) return;
+__global__ void __launch_bounds__(kExpThreads)
+expand_kernel(const uint2* __restrict__ ranges_s, const uint32_t* __restrict__ cpay, const ushort4* __restrict__ rect,
+              const uint2* __restrict__ ranges, uint32_t* __restrict__ payload, int tiles_x, int tiles_y, int snx,
+              int lw, int lh, const uint32_t* __restrict__ abort) {
+  __shared__ uint32_t s_g[2][kExpThreads];
+  __shared__ uint2 s_r[2][kExpThreads];
+  if (abort && *abort) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* A = s_dyn;
-  uint32_t* B = s_dyn + smem_items;
-  if (L > smem_items) { A = scratch_a + rg.x; B = scratch_b + rg.x; }  // long segment: global scratch
+  const int per_super = 1 << (lw + lh - 4);  // CTAs per super-tile (a super-tile has at least 16 tiles)
+  const int s = blockIdx.x / per_super, sub = blockIdx.x - s * per_super;
+  const int lt = sub * kExpWarps + warp;     // tile inside the super-tile, row-major
+  const uint32_t tx = (uint32_t)(((s % snx) << lw) + (lt & ((1 << lw) - 1)));
+  const uint32_t ty = (uint32_t)(((s / snx) << lh) + (lt >> lw));
+  const bool valid = tx < (uint32_t)tiles_x && ty < (uint32_t)tiles_y;
+  const uint2 rs = ranges_s[s];
+  const uint32_t len = rs.y - rs.x;
+  const uint32_t* list = cpay + rs.x;
+  uint32_t out = valid ? ranges[ty * (uint32_t)tiles_x + tx].x : 0u;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (uint32_t i = tid; i < L; i += kTsThreads) A[i] = rank[payload[rg.x + i]];
-  if (L > 1) {
-    // contiguous slice per warp, a multiple of 32 items
-    const uint32_t per_warp = ((L + kTsWarps * 32 - 1) / (kTsWarps * 32)) * 32;
-    const uint32_t w0 = min(L, (uint32_t)warp * per_warp), w1 = min(L, w0 + per_warp);
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (int shift = 0; shift < rank_bits; shift += kTsBits) {
-      for (int t = tid; t < kTsWarps * kTsBins; t += kTsThreads) (&s_cnt[0][0])[t] = 0;
-      __syncthreads();
-      // 1. per-warp digit histogram (one shared atomic per distinct digit of a 32-item step)
-      for (uint32_t b = w0; b < w1; b += 32) {
-        const uint32_t i = b + lane;
-        const uint32_t d = i < w1 ? (A[i] >> shift) & (kTsBins - 1) : 0xFFFFu;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (i < w1 && (peers & lt_mask) == 0u) s_cnt[warp][d] += (uint32_t)__popc(peers);
-        __syncwarp();
-      }
-      __syncthreads();
-      // 2. exclusive scan over (digit, warp): thread d owns digit d
-      uint32_t local = 0;
-#pragma unroll
-      for (int w = 0; w < kTsWarps; ++w) local += s_cnt[w][tid];
-      uint32_t inc = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      s_part[tid] = inc;
-      __syncthreads();
-      uint32_t run = inc - local;
-      for (int w = 0; w < warp; ++w) run += s_part[w * 32 + 31];
-#pragma unroll
-      for (int w = 0; w < kTsWarps; ++w) {
-        const uint32_t v = s_cnt[w][tid];
-        s_cnt[w][tid] = run;
-        run += v;
-      }
-      __syncthreads();
-      // 3. stable scatter: same walk, the counter row now holds the running output position
-      for (uint32_t b = w0; b < w1; b += 32) {
-        const uint32_t i = b + lane;
-        const uint32_t v = i < w1 ? A[i] : 0u;
-        const uint32_t d = i < w1 ? (v >> shift) & (kTsBins - 1) : 0xFFFFu;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        uint32_t base = 0;
-        const int leader = __ffs(peers) - 1;
-        if (i < w1 && lane == leader) {
-          base = s_cnt[warp][d];
-          s_cnt[warp][d] = base + (uint32_t)__popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (i < w1) B[base + __popc(peers & lt_mask)] = v;
-        __syncwarp();
-      }
-      __syncthreads();
-      uint32_t* tswap = A; A = B; B = tswap;
+  uint32_t g_next = 0;
+  uint2 r_next = make_uint2(1u, 1u);
+  auto fetch = [&](uint32_t w0) {
+    if (w0 + tid < len) {
+      g_next = list[w0 + tid];
+      r_next = *reinterpret_cast<const uint2*>(rect + g_next);  // (tx0 | tx1 << 16, ty0 | ty1 << 16)
     }
-  } else {
-    __syncthreads();
+  };
+  fetch(0);
+  for (uint32_t w0 = 0, it = 0; w0 < len; w0 += kExpThreads, ++it) {
+    const int buf = (int)(it & 1u);
+    s_g[buf][tid] = g_next;
+    s_r[buf][tid] = r_next;
+    __syncthreads();  // also orders the reads of this buffer two windows ago before the writes above
+    fetch(w0 + kExpThreads);
+    const uint32_t cnt = len - w0 < (uint32_t)kExpThreads ? len - w0 : (uint32_t)kExpThreads;
+    if (valid) {
+      for (uint32_t c = 0; c < cnt; c += 32) {
+        const uint32_t e = c + lane;
+        bool hit = false;
+        if (e < cnt) {
+          const uint2 r = s_r[buf][e];
+          hit = (r.x & 0xFFFFu) <= tx && tx <= (r.x >> 16) && (r.y & 0xFFFFu) <= ty && ty <= (r.y >> 16);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) payload[out + (uint32_t)__popc(m & lt_mask)] = s_g[buf][e];
+        out += (uint32_t)__popc(m);
+      }
+    }
   }
-  for (uint32_t i = tid; i < L; i += kTsThreads) payload[rg.x + i] = order[A[i]];
 }
 
-int launch_tile_sort(const uint2* ranges, int tiles, const uint32_t* rank, const uint32_t* order, uint32_t* payload,
-                     int rank_bits, uint32_t* scratch_a, uint32_t* scratch_b, cudaStream_t st) {
-  if (tiles <= 0) return 0;
-  const uint32_t smem_items = 4096;  // 2 x 16 KB of dynamic shared memory: lists up to 4 096 entries stay on the SM
-  const size_t dyn = (size_t)smem_items * 2 * sizeof(uint32_t);
-  tile_sort_kernel<<<(unsigned)tiles, kTsThreads, dyn, st>>>(ranges, rank, order, payload, rank_bits, smem_items,
-                                                            scratch_a, scratch_b);
+int launch_expand(const uint2* ranges_s, const uint32_t* cpay, const ushort4* rect, const uint2* ranges,
+                  uint32_t* payload, FrameGeom geom, SuperGeom sg, const uint32_t* abort, cudaStream_t st) {
+  const int supers = sg.nx * sg.ny;
+  if (supers <= 0 || sg.lw + sg.lh < 4) return 0;
+  const unsigned blocks = (unsigned)supers << (sg.lw + sg.lh - 4);
+  expand_kernel<<<blocks, kExpThreads, 0, st>>>(ranges_s, cpay, rect, ranges, payload, geom.tiles_x, geom.tiles_y, sg.nx,
+                                                sg.lw, sg.lh, abort);
   return (int)cudaGetLastError();
 }
 
@@ -481,8 +457,7 @@ constexpr int kStatThreads = 1024;
 
 __global__ void __launch_bounds__(kStatThreads)
 tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, int tiles_y,
-                  uint32_t* __restrict__ tile_hist, uint2* __restrict__ ranges, uint32_t* __restrict__ k_total,
-                  const uint32_t* __restrict__ m_counter, volatile uint32_t* host_mailbox, uint32_t seq) {
+                  uint32_t* __restrict__ tile_hist, uint2* __restrict__ ranges, uint32_t* ctl, StatsPost post) {
   extern __shared__ int32_t s_grid[];
   __shared__ uint32_t s_hist[4][kRadix];
   __shared__ uint32_t s_warp[kStatThreads / 32];
@@ -580,34 +555,49 @@ tile_stats_kernel(int32_t* __restrict__ grid_global, int use_smem, int tiles_x, 
   for (int p = 1; p < 4; ++p)
     if (acc[p - 1]) atomicAdd(&s_hist[p][cur[p - 1]], acc[p - 1]);
   __syncthreads();
-  for (int t = tid; t < 4 * kRadix; t += kStatThreads) tile_hist[t] = (&s_hist[0][0])[t];
-  if (tid == 0) {  // 64-bit total: the host rejects K >= 2^32 (positions are u32)
-    k_total[0] = (uint32_t)total64;
-    k_total[1] = (uint32_t)(total64 >> 32);
-    if (host_mailbox) {
-      // Mailbox in mapped pinned host memory: the host polls word 4 and learns M and K while the depth sort is
-      // still running on the main stream, so the read-back it needs to size the key buffers costs no bubble.
-      host_mailbox[0] = *m_counter;
-      host_mailbox[1] = m_counter[kCtlVisible];  // V: Gaussians with tiles (sizes the rank field of 32-bit keys)
-      host_mailbox[2] = (uint32_t)total64;
-      host_mailbox[3] = (uint32_t)(total64 >> 32);
-      __threadfence_system();
-      host_mailbox[4] = seq;
+  if (tile_hist)
+    for (int t = tid; t < 4 * kRadix; t += kStatThreads) tile_hist[t] = (&s_hist[0][0])[t];
+  if (tid == 0) {  // 64-bit totals: the host rejects K >= 2^32 (positions are u32)
+    uint32_t* mine = ctl + (post.level ? kCtlKs : kCtlK);
+    mine[0] = (uint32_t)total64;
+    mine[1] = (uint32_t)(total64 >> 32);
+    if (post.enabled) {
+      // K = tile instances, Ks = super-tile instances (= K when the frame is binned in one level)
+      unsigned long long k = total64, ks = total64;
+      if (post.level) k = ((unsigned long long)ctl[kCtlK + 1] << 32) | ctl[kCtlK];  // written by the previous launch
+      else { ctl[kCtlKs] = (uint32_t)total64; ctl[kCtlKs + 1] = (uint32_t)(total64 >> 32); }
+      // The kernels that consume these counts are ALREADY queued, with grids and buffers sized from the context's
+      // capacities: if a count does not fit they must not run (the host grows the buffers and re-queues them).
+      const uint32_t ab = (k > post.cap_k || ks > post.cap_ks) ? 1u : 0u;
+      ctl[kCtlAbort] = ab;
+      if (post.mailbox) {
+        // Mailbox in mapped pinned host memory: the host learns M, K and the verdict without draining the stream.
+        volatile uint32_t* box = post.mailbox;
+        box[0] = ctl[kCtlM];
+        box[1] = ctl[kCtlVisible];  // V: Gaussians with tiles
+        box[2] = (uint32_t)k;
+        box[3] = (uint32_t)(k >> 32);
+        box[5] = ab;
+        box[6] = (uint32_t)ks;
+        box[7] = (uint32_t)(ks >> 32);
+        __threadfence_system();
+        box[4] = post.seq;
+      }
     }
   }
 }
 
-int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,
-                      const uint32_t* m_counter, uint32_t* host_mailbox, uint32_t seq, cudaStream_t st) {
-  if (geom.tiles_x <= 0 || geom.tiles_y <= 0) return 0;
-  const size_t bytes = (size_t)(geom.tiles_x + 1) * (size_t)(geom.tiles_y + 1) * sizeof(int32_t);
+int launch_tile_stats(int32_t* diff_grid, int tiles_x, int tiles_y, uint32_t* tile_hist, uint2* ranges, uint32_t* ctl,
+                      const StatsPost& post, cudaStream_t st) {
+  if (tiles_x <= 0 || tiles_y <= 0) return 0;
+  const size_t bytes = (size_t)(tiles_x + 1) * (size_t)(tiles_y + 1) * sizeof(int32_t);
   const int use_smem = bytes <= 200 * 1024;
   if (use_smem && bytes > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(tile_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
   }
-  tile_stats_kernel<<<1, kStatThreads, use_smem ? bytes : 0, st>>>(diff_grid, use_smem, geom.tiles_x, geom.tiles_y,
-                                                                  tile_hist, ranges, k_total, m_counter, host_mailbox, seq);
+  tile_stats_kernel<<<1, kStatThreads, use_smem ? bytes : 0, st>>>(diff_grid, use_smem, tiles_x, tiles_y, tile_hist,
+                                                                  ranges, ctl, post);
   return (int)cudaGetLastError();
 }
 

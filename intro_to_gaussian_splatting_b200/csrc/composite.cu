@@ -19,6 +19,7 @@
 //
 // Roofline: issue slots (fp32 FMA/ALU + MUFU.EX2), not HBM: ~20 warp-instructions per
 // (warp, Gaussian) step; HBM traffic is 4 B payload + 48 B record per instance + 12 B per pixel.
+#include <cmath>
 #include <cstdlib>
 
 #include "gsb_internal.cuh"
@@ -38,13 +39,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct CompositeArgs {
   int width, height, tiles_x, tiles_y;
   float min_weight, alpha_max;
+  float cull_log2;  // warp-level skip threshold as log2(alpha); -inf = never skip
 };
 
 template <int kSem>
 __global__ void __launch_bounds__(256)
 composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
                  const float4* __restrict__ rec, const float4* __restrict__ bbox, float* __restrict__ image,
-                 const __grid_constant__ CompositeArgs a) {
+                 const uint32_t* __restrict__ abort, const __grid_constant__ CompositeArgs a) {
+  if (abort && *abort) return;
   __shared__ float4 s0[kBatch];  // mx, my, a, b      (a b; c d) = -0.5 * inverse covariance
   __shared__ float4 s1[kBatch];  // c, d, op, r
   __shared__ float2 s2[kBatch];  // g, b
@@ -141,8 +144,19 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 // Staging: records are copied global->shared with cp.async (LDGSTS, 3 x 16 B per record, no register
 // staging) into a double buffer, one batch ahead of the blend loop; the payload index of the batch
 // after that is prefetched into a register so the cp.async addresses are ready when the buffer frees.
-// Slots past the end of the list are filled with a null record (log2 opacity -inf => alpha = 0 => exact no-op)
-// so the blend loop needs no tail handling.
+//
+// Per-warp culling.  The reference has no per-pixel bounding-box test: every pixel of a
+// tile evaluates every Gaussian of the tile's list, and for a large share of those steps alpha is exactly 0 in
+// fp32 (ex2.approx.ftz underflows below 2^-126) or far below anything fp32 can see.  Once a batch has landed, each
+// thread computes for its two records a CONSERVATIVE upper bound of  power * log2(e) + log2(opacity)  over each
+// warp's 16x8 pixel rectangle: the exponent is a concave quadratic in the pixel offset, so its maximum over a
+// rectangle is 0 when the centre is inside and otherwise the best of four 1-D edge maxima; a rounding margin
+// proportional to the magnitude of the cancelling terms covers the difference between the real-valued quadratic
+// and the kernel's (the reference's) fp32 evaluation order, so ill-conditioned conics are simply never culled.
+// One ballot per (record slot, warp footprint) turns the verdicts into a 128-bit survivor mask per warp and
+// batch, and the blend loop walks the set bits only.  With cull_alpha = 0 only steps whose alpha is exactly zero
+// are skipped (bit-identical frames); with cull_alpha = t > 0 a skipped step would have changed a pixel by less
+// than t (T and live are untouched for alpha < 2^-25), so the frame differs by < t * (list length).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastThreads = 64;
 constexpr int kFastBatch = 128;                        // records per stage
@@ -160,14 +174,46 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// kAux (save_for_backward): also records, per pixel, how many Gaussians were blended (the list prefix [0, n)) and
-// the transmittance after the last of them -- what the back-to-front gradient pass starts from (backward.cu).
+// max over t in [lo, hi] of  q t^2 + s t + c0  for q < 0;  rq = 1 / (2 q)
+__device__ __forceinline__ float edge_max(float q, float s, float lo, float hi, float rq, float c0) {
+  const float t = fminf(fmaxf(-s * rq, lo), hi);
+  return fmaf(fmaf(q, t, s), t, c0);
+}
+
+// May any pixel of the rectangle dx in [dxl, dxh], dy in [dyl, dyh] (offsets mean - pixel) see
+// exp2(power * log2e + l2op) >= 2^thr ?  (A B; C D) = -0.5 * inverse covariance.  Conservative: answers true
+// whenever it cannot prove otherwise (indefinite or non-finite conic, NaNs, large cancellation).
+__device__ __forceinline__ bool may_contribute(float A, float B, float C, float D, float l2op, float dxl, float dxh,
+                                               float dyl, float dyh, float thr) {
+  const float S = B + C;
+  const bool ok = A < 0.f && A > -1e30f && D < 0.f && D > -1e30f && fmaf(4.f * A, D, -S * S) > 0.f &&
+                  fabsf(dxl) < 1e30f && fabsf(dyl) < 1e30f;
+  const bool inside = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;
+  const float rA = __frcp_rn(2.f * A), rD = __frcp_rn(2.f * D);
+  const float g1 = edge_max(D, S * dxl, dyl, dyh, rD, A * dxl * dxl);
+  const float g2 = edge_max(D, S * dxh, dyl, dyh, rD, A * dxh * dxh);
+  const float h1 = edge_max(A, S * dyl, dxl, dxh, rA, D * dyl * dyl);
+  const float h2 = edge_max(A, S * dyh, dxl, dxh, rA, D * dyh * dyh);
+  const float ub = inside ? 0.f : fmaxf(fmaxf(g1, g2), fmaxf(h1, h2));
+  const float ax = fmaxf(fabsf(dxl), fabsf(dxh)), ay = fmaxf(fabsf(dyl), fabsf(dyh));
+  // |rounding error| of the fp32 evaluation in the blend loop (and of this bound) <= 2^-21 * sum of |terms|
+  const float mag = fmaf(fabsf(A) * ax, ax, fmaf((fabsf(B) + fabsf(C)) * ax, ay, fabsf(D) * ay * ay));
+  const float arg = fmaf(ub + fmaf(mag, 4.76837158e-7f, 1e-3f), 1.4426950408889634f, l2op);
+  return !ok || !(arg < thr);
+}
+
+// kAux (save_for_backward): also records, per pixel, the length of the list prefix that reached the pixel (index of
+// the last blended Gaussian + 1) and the transmittance after it -- what the back-to-front gradient pass starts
+// from (backward.cu).
 template <bool kAux>
 __global__ void __launch_bounds__(kFastThreads)
 composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
                       const float4* __restrict__ rec, float* __restrict__ image, float* __restrict__ aux_t,
-                      uint32_t* __restrict__ aux_n, const __grid_constant__ CompositeArgs a) {
+                      uint32_t* __restrict__ aux_n, const uint32_t* __restrict__ abort,
+                      const __grid_constant__ CompositeArgs a) {
   __shared__ __align__(16) float4 sm[2][kFastBatch * 3];
+  __shared__ __align__(16) uint32_t s_mask[2][2][kFastBatch / 32];  // [buffer][warp footprint][survivor bits]
+  if (abort && *abort) return;  // the lists do not exist: the host re-queues the frame's tail (gsb_api.cu)
 
   const int tile = blockIdx.x;
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
@@ -177,6 +223,10 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   const float fx = (float)px;
   const float fy0 = (float)py0, fy1 = (float)(py0 + 1), fy2 = (float)(py0 + 2), fy3 = (float)(py0 + 3);
   const float minw = a.min_weight;
+  const float cull = a.cull_log2;
+  // pixel rectangles of the two warps (columns shared)
+  const float rx0 = (float)(tx * kTile), rx1 = rx0 + (float)(kTile - 1);
+  const float ry0 = (float)(ty * kTile), ry1 = ry0 + 7.f, ry2 = ry0 + 8.f, ry3 = ry0 + 15.f;
 
   const uint2 rg = ranges[tile];
   const uint32_t len = rg.y - rg.x;
@@ -190,8 +240,6 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;          // kAux only
   float tf0 = 1.f, tf1 = 1.f, tf2 = 1.f, tf3 = 1.f;  // kAux only
 
-  const float4 null0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 null1 = make_float4(0.f, 0.f, -INFINITY, 0.f);  // log2(opacity) = -inf => alpha = 0 => exact no-op
   // stage batch `b` (records b*128 .. b*128+127) into buffer `buf`; idx[] holds this thread's payload indices
   uint32_t idx[kFastPerThread];
   auto load_idx = [&](uint32_t b) {
@@ -205,14 +253,28 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 #pragma unroll
     for (int j = 0; j < kFastPerThread; ++j) {
       float4* dst = &sm[buf][(j * kFastThreads + tid) * 3];
-      if (idx[j] != 0xFFFFFFFFu) {
+      if (idx[j] != 0xFFFFFFFFu) {  // slots past the end of the list are never read: their survivor bit is 0
         const float4* src = rec + 3 * (size_t)idx[j];
         cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
-      } else {
-        dst[0] = null0; dst[1] = null1; dst[2] = null0;
       }
     }
     cp_async_commit();
+  };
+  // survivor masks of batch `b` (resident in buffer `buf`): record slot j*64 + tid is bit `lane` of word 2j + warp
+  auto build_masks = [&](int buf, uint32_t b) {
+#pragma unroll
+    for (int j = 0; j < kFastPerThread; ++j) {
+      const int r = j * kFastThreads + tid;
+      bool k0 = false, k1 = false;
+      if (b * kFastBatch + r < len) {
+        const float4 q0 = sm[buf][r * 3], q1 = sm[buf][r * 3 + 1];
+        const float dxl = q0.x - rx1, dxh = q0.x - rx0;
+        k0 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry1, q0.y - ry0, cull);
+        k1 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry3, q0.y - ry2, cull);
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+      if (lane == 0) { s_mask[buf][0][2 * j + warp] = m0; s_mask[buf][1][2 * j + warp] = m1; }
+    }
   };
 
   const uint32_t nb = (len + kFastBatch - 1) / kFastBatch;
@@ -222,46 +284,56 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   for (uint32_t b = 0; b < nb; ++b) {
     const int buf = (int)(b & 1);
     cp_async_wait<0>();
-    __syncthreads();  // batch b visible to all; everyone is done reading the other buffer
+    // batch b visible to all; everyone is done reading the other buffer; stop when no pixel of the tile is live
+    if (!__syncthreads_or(warp_live)) break;
     if (b + 1 < nb) {
       stage(buf ^ 1);
       if (b + 2 < nb) load_idx(b + 2);
     }
+    build_masks(buf, b);
+    __syncthreads();
     if (warp_live) {
-      const float4* p = sm[buf];
 #pragma unroll 1
-      for (int i = 0; i < kFastBatch; i += kFastUnroll) {
+      for (int q = 0; q < kFastBatch / 32; ++q) {
+        uint32_t m = s_mask[buf][warp][q];
+        const float4* pq = sm[buf] + q * 32 * 3;
+        const uint32_t nbase = b * kFastBatch + q * 32 + 1;  // kAux: list position + 1 of bit 0
+        while (m) {
 #pragma unroll
-        for (int u = 0; u < kFastUnroll; ++u) {
-          const float4 q0 = p[0];  // mx, my, a, b
-          const float4 q1 = p[1];  // c, d, op, r
-          const float2 q2 = *reinterpret_cast<const float2*>(p + 2);  // g, b
-          p += 3;
-          const float dx = q0.x - fx;
-          const float ta_ = __fmul_rn(dx, q0.z), tb_ = __fmul_rn(dx, q0.w);
+          for (int u = 0; u < kFastUnroll; ++u) {
+            if (m == 0u) break;
+            const int i = __ffs(m) - 1;
+            m &= m - 1u;
+            const float4* p = pq + i * 3;
+            const float4 q0 = p[0];  // mx, my, a, b
+            const float4 q1 = p[1];  // c, d, log2(op), r
+            const float2 q2 = *reinterpret_cast<const float2*>(p + 2);  // g, b
+            const float dx = q0.x - fx;
+            const float ta_ = __fmul_rn(dx, q0.z), tb_ = __fmul_rn(dx, q0.w);
 #define GSB_PIXEL_STEP(FY, T, LIVE, R, G, B, NC, TF)                                       \
-          {                                                                                \
-            const float dy = q0.y - FY;                                                    \
-            const float u0 = __fmaf_rn(dy, q1.x, ta_);                                     \
-            const float u1 = __fmaf_rn(dy, q1.y, tb_);                                     \
-            const float pw = __fadd_rn(__fmul_rn(u0, dx), __fmul_rn(u1, dy));              \
-            const float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z)); /* q1.z = log2(op) */ \
-            const float ta = T * al;                                                       \
-            T = T - ta;                                                                    \
-            LIVE = LIVE && (T >= minw);                                                    \
-            if (LIVE) { R = fmaf(ta, q1.w, R); G = fmaf(ta, q2.x, G); B = fmaf(ta, q2.y, B); } \
-            if (kAux) { if (LIVE) { NC += 1; TF = T; } }                                   \
-          }
-          GSB_PIXEL_STEP(fy0, T0, l0, r0, g0, b0, n0, tf0)
-          GSB_PIXEL_STEP(fy1, T1, l1, r1, g1, b1, n1, tf1)
-          GSB_PIXEL_STEP(fy2, T2, l2, r2, g2, b2, n2, tf2)
-          GSB_PIXEL_STEP(fy3, T3, l3, r3, g3, b3, n3, tf3)
+            {                                                                              \
+              const float dy = q0.y - FY;                                                  \
+              const float u0 = __fmaf_rn(dy, q1.x, ta_);                                   \
+              const float u1 = __fmaf_rn(dy, q1.y, tb_);                                   \
+              const float pw = __fadd_rn(__fmul_rn(u0, dx), __fmul_rn(u1, dy));            \
+              const float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z)); /* q1.z = log2(op) */ \
+              const float ta = T * al;                                                     \
+              T = T - ta;                                                                  \
+              LIVE = LIVE && (T >= minw);                                                  \
+              if (LIVE) { R = fmaf(ta, q1.w, R); G = fmaf(ta, q2.x, G); B = fmaf(ta, q2.y, B); } \
+              if (kAux) { if (LIVE) { NC = nbase + (uint32_t)i; TF = T; } }                \
+            }
+            GSB_PIXEL_STEP(fy0, T0, l0, r0, g0, b0, n0, tf0)
+            GSB_PIXEL_STEP(fy1, T1, l1, r1, g1, b1, n1, tf1)
+            GSB_PIXEL_STEP(fy2, T2, l2, r2, g2, b2, n2, tf2)
+            GSB_PIXEL_STEP(fy3, T3, l3, r3, g3, b3, n3, tf3)
 #undef GSB_PIXEL_STEP
+          }
+          if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) { warp_live = false; m = 0u; }
         }
-        if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) { warp_live = false; break; }
+        if (!warp_live) break;
       }
     }
-    if (!__syncthreads_or(warp_live)) break;  // also orders this batch's reads before the next overwrite
   }
   cp_async_wait<0>();
   if (px < a.width) {
@@ -272,175 +344,47 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     if (py0 + 2 < a.height) { o[2 * row] = r2; o[2 * row + 1] = g2; o[2 * row + 2] = b2; }
     if (py0 + 3 < a.height) { o[3 * row] = r3; o[3 * row + 1] = g3; o[3 * row + 2] = b3; }
     if (kAux) {
-      // a null record (tail padding of the last batch) passes the LIVE test with alpha = 0: clamp to the list
       const size_t p = (size_t)py0 * a.width + px, w = (size_t)a.width;
-      if (py0 < a.height) { aux_t[p] = tf0; aux_n[p] = min(n0, len); }
-      if (py0 + 1 < a.height) { aux_t[p + w] = tf1; aux_n[p + w] = min(n1, len); }
-      if (py0 + 2 < a.height) { aux_t[p + 2 * w] = tf2; aux_n[p + 2 * w] = min(n2, len); }
-      if (py0 + 3 < a.height) { aux_t[p + 3 * w] = tf3; aux_n[p + 3 * w] = min(n3, len); }
+      if (py0 < a.height) { aux_t[p] = tf0; aux_n[p] = n0; }
+      if (py0 + 1 < a.height) { aux_t[p + w] = tf1; aux_n[p + w] = n1; }
+      if (py0 + 2 < a.height) { aux_t[p + 2 * w] = tf2; aux_n[p + 2 * w] = n2; }
+      if (py0 + 3 < a.height) { aux_t[p + 3 * w] = tf3; aux_n[p + 3 * w] = n3; }
     }
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// REF_CPU path, packed-fp32 variant (Blackwell): the same 64-thread / 1x4-pixel-column mapping as
-// composite_fast_kernel, but the four pixels are processed as TWO PAIRS with the sm_100 dual-fp32
-// instructions (FFMA2 / FMUL2 / FADD2, PTX fma.rn.f32x2 ...).  Each packed op performs two IEEE-rn
-// operations, bit-identical to two scalar ones, for one issue slot -- and issue slots are what bound this
-// kernel (ncu: issue active 85 %, FMA pipe 65 %, DRAM 1 %).  Per pixel-step: ~12.5 SASS instructions
-// instead of 17.4.
-//
-// Packed operands must sit in aligned register pairs, so every per-Gaussian scalar that multiplies a pixel
-// pair is stored DUPLICATED in shared memory: a record is 5 x float4
-//     {mx,mx,my,my} {a,a,b,b} {c,c,d,d} {op,op,r,r} {g,g,bl,bl}            (a b; c d) = -0.5 * inv cov
-// read with five broadcast LDS.128 per thread-step.  cp.async cannot duplicate, so staging goes through
-// registers (one record per thread per batch of 64, prefetched one batch ahead, double-buffered in smem).
-//
-// Termination: live &= (T >= min_weight) per pixel as before; the colour FMAs are packed, so instead of
-// predicating them the blend weight is zeroed with FSEL when the pixel is no longer live.
-// ------------------------------------------------------------------------------------------------
-constexpr int kPkThreads = 64;
-constexpr int kPkBatch = 64;
-
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-
-__global__ void __launch_bounds__(kPkThreads)
-composite_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
-                        const float4* __restrict__ rec, float* __restrict__ image,
-                        const __grid_constant__ CompositeArgs a) {
-  __shared__ __align__(16) float4 sm[2][kPkBatch * 5];
-
-  const int tile = blockIdx.x;
-  const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int px = tx * kTile + (lane & 15);
-  const int py0 = ty * kTile + warp * 8 + (lane >> 4) * 4;
-  const float2 nfx = f2(-(float)px, -(float)px);
-  const float2 nfyA = f2(-(float)py0, -(float)(py0 + 1));
-  const float2 nfyB = f2(-(float)(py0 + 2), -(float)(py0 + 3));
-  const float2 kLog2e = f2(1.4426950408889634f, 1.4426950408889634f);
-  const float2 kNeg1 = f2(-1.f, -1.f);
-  const float minw = a.min_weight;
-
-  const uint2 rg = ranges[tile];
-  const uint32_t len = rg.y - rg.x;
-  const uint32_t* pl = payload + rg.x;
-
-  bool l0 = px < a.width && py0 < a.height, l1 = px < a.width && py0 + 1 < a.height;
-  bool l2 = px < a.width && py0 + 2 < a.height, l3 = px < a.width && py0 + 3 < a.height;
-  float2 TA = f2(1.f, 1.f), TB = f2(1.f, 1.f);
-  float2 RA = f2(0.f, 0.f), GA = RA, BA = RA, RB = RA, GB = RA, BB = RA;
-
-  // register-staged prefetch: this thread's record of the next batch
-  float4 p0 = make_float4(0, 0, 0, 0), p1 = make_float4(0.f, 0.f, -INFINITY, 0.f), p2 = p0;
-  auto fetch = [&](uint32_t b) {
-    const uint32_t slot = b * kPkBatch + tid;
-    p0 = make_float4(0, 0, 0, 0); p2 = p0;
-    p1 = make_float4(0.f, 0.f, -INFINITY, 0.f);  // null record: log2(opacity) = -inf => alpha 0 => exact no-op
-    if (slot < len) {
-      const float4* src = rec + 3 * (size_t)pl[slot];
-      p0 = src[0]; p1 = src[1]; p2 = src[2];
-    }
-  };
-  auto stash = [&](int buf) {
-    float4* d = &sm[buf][tid * 5];
-    d[0] = make_float4(p0.x, p0.x, p0.y, p0.y);  // mx mx my my
-    d[1] = make_float4(p0.z, p0.z, p0.w, p0.w);  // a a b b
-    d[2] = make_float4(p1.x, p1.x, p1.y, p1.y);  // c c d d
-    d[3] = make_float4(p1.z, p1.z, p1.w, p1.w);  // op op r r
-    d[4] = make_float4(p2.x, p2.x, p2.y, p2.y);  // g g bl bl
-  };
-
-  const uint32_t nb = (len + kPkBatch - 1) / kPkBatch;
-  if (nb > 0) { fetch(0); stash(0); }
-  if (nb > 1) fetch(1);
-  bool warp_live = true;
-  for (uint32_t b = 0; b < nb; ++b) {
-    const int buf = (int)(b & 1);
-    __syncthreads();  // batch b visible; everyone is done reading the other buffer
-    if (b + 1 < nb) {
-      stash(buf ^ 1);
-      if (b + 2 < nb) fetch(b + 2);
-    }
-    if (warp_live) {
-      const float4* p = sm[buf];
-#pragma unroll 1
-      for (int i = 0; i < kPkBatch; i += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
-          p += 5;
-          const float2 dx = __fadd2_rn(f2(q0.x, q0.y), nfx);            // (dx, dx)
-          const float2 ta_ = __fmul2_rn(dx, f2(q1.x, q1.y));            // (dx*a, dx*a)
-          const float2 tb_ = __fmul2_rn(dx, f2(q1.z, q1.w));            // (dx*b, dx*b)
-          const float2 my = f2(q0.z, q0.w), cc = f2(q2.x, q2.y), dd = f2(q2.z, q2.w);
-          const float2 op = f2(q3.x, q3.y), cr = f2(q3.z, q3.w), cg = f2(q4.x, q4.y), cb = f2(q4.z, q4.w);
-#define GSB_PAIR_STEP(NFY, T, LA, LB, R, G, B)                                                   \
-          {                                                                                      \
-            const float2 dy = __fadd2_rn(my, NFY);                                               \
-            const float2 u0 = __ffma2_rn(dy, cc, ta_);                                           \
-            const float2 u1 = __ffma2_rn(dy, dd, tb_);                                           \
-            /* ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS, even with */ \
-            /* --fmad=false); the reference sum is UNFUSED, so the add is done with scalar FADDs */ \
-            const float2 m0 = __fmul2_rn(u0, dx), m1 = __fmul2_rn(u1, dy);                       \
-            const float2 pw = f2(__fadd_rn(m0.x, m1.x), __fadd_rn(m0.y, m1.y));                  \
-            const float2 e = __ffma2_rn(pw, kLog2e, op); /* op = (log2(op), log2(op)) */          \
-            const float2 al = f2(ex2_approx(e.x), ex2_approx(e.y));                              \
-            float2 ta = __fmul2_rn(T, al);                                                       \
-            T = __ffma2_rn(ta, kNeg1, T);                                                        \
-            LA = LA && (T.x >= minw);                                                            \
-            LB = LB && (T.y >= minw);                                                            \
-            ta.x = LA ? ta.x : 0.f;                                                              \
-            ta.y = LB ? ta.y : 0.f;                                                              \
-            R = __ffma2_rn(ta, cr, R); G = __ffma2_rn(ta, cg, G); B = __ffma2_rn(ta, cb, B);     \
-          }
-          GSB_PAIR_STEP(nfyA, TA, l0, l1, RA, GA, BA)
-          GSB_PAIR_STEP(nfyB, TB, l2, l3, RB, GB, BB)
-#undef GSB_PAIR_STEP
-        }
-        if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) { warp_live = false; break; }
-      }
-    }
-    if (!__syncthreads_or(warp_live)) break;
-  }
-  if (px < a.width) {
-    float* o = image + ((size_t)py0 * a.width + px) * 3;
-    const size_t row = (size_t)a.width * 3;
-    if (py0 < a.height) { o[0] = RA.x; o[1] = GA.x; o[2] = BA.x; }
-    if (py0 + 1 < a.height) { o[row] = RA.y; o[row + 1] = GA.y; o[row + 2] = BA.y; }
-    if (py0 + 2 < a.height) { o[2 * row] = RB.x; o[2 * row + 1] = GB.x; o[2 * row + 2] = BB.x; }
-    if (py0 + 3 < a.height) { o[3 * row] = RB.y; o[3 * row + 1] = GB.y; o[3 * row + 2] = BB.y; }
   }
 }
 
 
 }  // namespace
 
+static float cull_threshold_log2(const GsbParams& prm) {
+  // cull_alpha < 0: no warp-level skipping; 0: skip only what is exactly zero in fp32 (ex2.approx.ftz flushes below
+  // 2^-126; one binade of slack for its own rounding); > 0: skip when every alpha of the warp is below it
+  if (prm.cull_alpha < 0.f) return -INFINITY;
+  if (prm.cull_alpha == 0.f) return -127.f;
+  const float l = log2f(prm.cull_alpha);
+  return l < -127.f ? -127.f : l;
+}
+
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
-                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, cudaStream_t st) {
+                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, const uint32_t* abort,
+                     cudaStream_t st) {
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
-  CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max};
-  // GSB_COMPOSITE=2 selects the packed-fp32x2 variant (A/B knob).  Measured on B200, config 3: 432 us vs 424 us
-  // for the scalar kernel -- FFMA2/FMUL2/FADD2 halve the issue slots (289 M vs 387 M warp instructions) but
-  // occupy the FMA pipe for two cycles each, so the pipe-bound time is unchanged (profiles/r1_summary.md).
-  static const int variant = [] { const char* e = std::getenv("GSB_COMPOSITE"); return e ? std::atoi(e) : 1; }();
+  CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max,
+                  cull_threshold_log2(prm)};
   if (aux_t && aux_n)
-    composite_fast_kernel<true><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, aux_t, aux_n, a);
-  else if (variant == 2)
-    composite_packed_kernel<<<tiles, kPkThreads, 0, st>>>(ranges, payload, rec, image, a);
+    composite_fast_kernel<true><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, aux_t, aux_n, abort, a);
   else
-    composite_fast_kernel<false><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, nullptr, nullptr, a);
+    composite_fast_kernel<false><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, nullptr, nullptr, abort, a);
   return (int)cudaGetLastError();
 }
 
 int launch_composite_cu(const uint2* ranges, const uint32_t* payload, const float4* rec, const float4* bbox,
-                        float* image, FrameGeom geom, const GsbParams& prm, cudaStream_t st) {
+                        float* image, FrameGeom geom, const GsbParams& prm, const uint32_t* abort, cudaStream_t st) {
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
-  CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max};
-  composite_kernel<GSB_SEM_REF_CU><<<tiles, 256, 0, st>>>(ranges, payload, rec, bbox, image, a);
+  CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max, -INFINITY};
+  composite_kernel<GSB_SEM_REF_CU><<<tiles, 256, 0, st>>>(ranges, payload, rec, bbox, image, abort, a);
   return (int)cudaGetLastError();
 }
 
@@ -459,7 +403,7 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
               const float* __restrict__ min_y, const float* __restrict__ max_y, const float* __restrict__ opacity,
               FrameGeom geom, int sem, int T, uint32_t* __restrict__ depth_key, float4* __restrict__ rec,
               float4* __restrict__ bbox, ushort4* __restrict__ rect, uint32_t* __restrict__ count,
-              int32_t* __restrict__ diff_grid) {
+              int32_t* __restrict__ diff_grid, int32_t* __restrict__ super_grid, SuperGeom sg) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float mx = means[2 * i], my = means[2 * i + 1];
@@ -497,15 +441,23 @@ ingest_kernel(int64_t m, const float* __restrict__ means, const float* __restric
   uint32_t cnt = 0;
   if (!nan && tx1 >= tx0 && ty1 >= ty0) cnt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
   rect[i] = cnt ? make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1)
-                : make_ushort4(0, 0, 0, 0);
+                : make_ushort4(1, 0, 1, 0);  // tx1 < tx0: touches no tile
   count[i] = cnt;
   depth_key[i] = (uint32_t)i;
-  if (cnt) {  // same 2-D difference grid as the projection kernel (tile_stats_kernel turns it into ranges)
+  if (cnt) {  // same 2-D difference grids as the projection kernel (tile_stats_kernel turns them into ranges)
     const int gw = geom.tiles_x + 1;
     atomicAdd(&diff_grid[ty0 * gw + tx0], 1);
     atomicAdd(&diff_grid[ty0 * gw + tx1 + 1], -1);
     atomicAdd(&diff_grid[(ty1 + 1) * gw + tx0], -1);
     atomicAdd(&diff_grid[(ty1 + 1) * gw + tx1 + 1], 1);
+    if (super_grid) {
+      const int sx0 = tx0 >> sg.lw, sx1 = (tx1 >> sg.lw) + 1, sy0 = ty0 >> sg.lh, sy1 = (ty1 >> sg.lh) + 1;
+      const int gs = sg.nx + 1;
+      atomicAdd(&super_grid[sy0 * gs + sx0], 1);
+      atomicAdd(&super_grid[sy0 * gs + sx1], -1);
+      atomicAdd(&super_grid[sy1 * gs + sx0], -1);
+      atomicAdd(&super_grid[sy1 * gs + sx1], 1);
+    }
   }
 }
 
@@ -513,11 +465,11 @@ int launch_ingest_preprocessed(int64_t m, const float* means, const float* color
                                const float* min_x, const float* max_x, const float* min_y, const float* max_y,
                                const float* opacity, FrameGeom geom, const GsbParams& prm, uint32_t* depth_key,
                                float4* rec, float4* bbox, ushort4* rect, uint32_t* count, int32_t* diff_grid,
-                               cudaStream_t st) {
+                               int32_t* super_grid, SuperGeom sg, cudaStream_t st) {
   if (m == 0) return 0;
   ingest_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(m, means, colors, conic, min_x, max_x, min_y, max_y,
                                                             opacity, geom, prm.semantics, prm.tile_size, depth_key,
-                                                            rec, bbox, rect, count, diff_grid);
+                                                            rec, bbox, rect, count, diff_grid, super_grid, sg);
   return (int)cudaGetLastError();
 }
 

@@ -1,17 +1,22 @@
 // gsb_api.cu -- the C ABI (include/gsb.h): context, scratch management, kernel-chain orchestration.
 //
-// Frame pipeline (one stream, no CPU work between kernels except ONE read-back of the tile-instance
-// count K, needed to size the key buffers and the sort grid):
+// Frame pipeline (one stream; tile statistics on an auxiliary stream):
 //
-//   FULL :  project -> scan(index order) -> [K] -> emit -> histogram + p x onesweep(K, 64-bit keys)
-//           -> ranges -> composite                          p = ceil((32 + tile_bits) / 8)
-//   SPLIT:  project -> histogram + 4 x onesweep(N, 32-bit depth keys) -> scan(depth order) -> [K]
-//           -> emit(depth order) -> histogram + ceil(tile_bits/8) x onesweep(K, tile digits only)
-//           -> ranges -> composite
+//   FULL :  project -> scan(index order) -> [K -> host] -> emit -> p x onesweep(K, 64-bit keys) -> composite
+//           p = ceil((32 + tile_bits) / 8); the literal pipeline of the north star, kept as the cross-check
+//   SPLIT:  project -> 4 x onesweep(N, 32-bit depth keys) -> scan(depth order, super-tile counts)
+//           -> emit(one key per SUPER-TILE instance) -> onesweep over the super-tile ids -> expand(per-tile lists)
+//           -> composite
 //
-// Both leave bit-identical sorted (key, payload) arrays: an LSD radix sort orders by the low (depth)
-// digits first, and every tile instance of a Gaussian shares those digits, so they can be sorted once
-// per Gaussian BEFORE the expansion instead of once per instance after it.
+// Both leave bit-identical per-tile lists: an LSD radix sort orders by the low (depth) digits first, and every tile
+// instance of a Gaussian shares those digits, so they can be sorted once per Gaussian BEFORE the expansion; what is
+// left is a stable partition by tile, done in two levels (binning.cu).
+//
+// SPLIT queues the WHOLE frame before the host reads anything data-dependent.  Grids and buffers are sized from
+// the context's capacities; tile_stats_kernel, which learns the counts, decides on the device whether they fit
+// (ctl[kCtlAbort]) and posts them to a mailbox in mapped pinned host memory.  The host picks them up after queueing
+// -- the GPU never waits for it -- and only when a count outgrew its buffer does it grow the buffer and queue the
+// tail of the frame again.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -22,11 +27,29 @@
 
 using namespace gsb;
 
+namespace gsb {
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+  if (dev >= 0 && dev < 64) cache[dev] = v;
+  return v;
+}
+}  // namespace gsb
+
 namespace {
 
+// device scratch owned by a context; released when the context is deleted (no list of members to keep in sync)
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
   int ensure(size_t bytes) {
     if (bytes <= cap) return GSB_OK;
     size_t want = bytes + bytes / 4 + 256;  // geometric growth
@@ -59,24 +82,42 @@ int ceil_log2(int64_t v) {
 }
 
 // control block, zeroed once per frame:
-//   [hdr 16: 0 = M, 1 = K mod 2^32 (scan), 2-3 = K (tile grid, 64-bit)] [hist 8 x 256: rows 0-3 depth digits, 4-7 tile digits]
-//   [difference grid (tiles_x+1)*(tiles_y+1)] [tile cursors (BINNED)] [emit scan status] [depth-sort tickets + status]
+//   [hdr 16: kCtl* words] [hist 8 x 256: rows 0-3 depth digits, 4-7 tile (FULL) / super-tile (SPLIT) digits]
+//   [difference grid (tiles_x+1)*(tiles_y+1)] [super-tile difference grid] [scan status] [depth-sort tickets + status]
 constexpr int kCtlHeaderWords = 16;
 constexpr int kCtlHistWords = kMaxPasses * kRadix;
 
 struct CtlLayout {
-  size_t hist, grid, cursor, scan, dsort, total;  // word offsets
+  size_t hist, grid, grid_s, scan, dsort, total;  // word offsets
 };
-CtlLayout ctl_layout(FrameGeom g, int64_t n_rows, size_t dsort_words) {
+CtlLayout ctl_layout(FrameGeom g, SuperGeom sg, int64_t n_rows, size_t dsort_words) {
   auto up4 = [](size_t w) { return (w + 3) & ~(size_t)3; };  // sections start 16-byte aligned (64-bit status words)
   CtlLayout L;
   L.hist = kCtlHeaderWords;
   L.grid = L.hist + kCtlHistWords;
-  L.cursor = up4(L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1));  // BINNED: one fill cursor per tile
-  L.scan = up4(L.cursor + (size_t)g.tiles_x * (size_t)g.tiles_y);
+  L.grid_s = up4(L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1));
+  L.scan = up4(L.grid_s + (size_t)(sg.nx + 1) * (size_t)(sg.ny + 1));
   L.dsort = up4(L.scan + scan_status_words(n_rows));
   L.total = up4(L.dsort + dsort_words);
   return L;
+}
+
+// Super-tile shape of SPLIT mode: start at 8 x 4 tiles and double the smaller side until the frame has at most
+// `max_supers` super-tiles (256: ONE radix pass over their ids; 1080p -> 15 x 17 = 255 super-tiles of 8 x 4 tiles,
+// 4K -> 15 x 17 of 16 x 8).  lw = lh = 0 switches the second level off (one key per tile instance).
+SuperGeom choose_super(FrameGeom g, int lw, int lh, int max_supers) {
+  SuperGeom s{lw, lh, 0, 0};
+  auto dims = [&] {
+    s.nx = (g.tiles_x + (1 << s.lw) - 1) >> s.lw;
+    s.ny = (g.tiles_y + (1 << s.lh) - 1) >> s.lh;
+  };
+  dims();
+  if (lw == 0 && lh == 0) return s;
+  while ((int64_t)s.nx * s.ny > max_supers && s.lw + s.lh < 30) {
+    if (s.lh < s.lw) ++s.lh; else ++s.lw;
+    dims();
+  }
+  return s;
 }
 
 }  // namespace
@@ -88,14 +129,18 @@ struct GsbContext {
   // per-Gaussian frame data
   DevBuf depth_key, rec, rect, count, offsets, bbox;
   DevBuf dbg_cov2d, dbg_conic, dbg_bbox;
-  DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, rank;
-  // per-instance
+  DevBuf ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b;
+  // per tile instance: FULL mode key/payload ping-pong; vals_a is also SPLIT's per-tile payload
   DevBuf keys_a, keys_b, vals_a, vals_b;
-  DevBuf ranges, control, control2;
+  // per super-tile instance (SPLIT): key ping-pong and the sorted Gaussian indices
+  DevBuf ckeys_a, ckeys_b, cvals;
+  DevBuf ranges, ranges_s, control, control2;
   DevBuf image, image2, scratch;
   // save_for_backward: per-pixel blended count / final transmittance of the last frame; gradient scratch
   DevBuf aux_t, aux_n, grad2d, grad_stage;
+  DevBuf host_stage[2];
   bool allow_keys32 = true;
+  int super_lw = 3, super_lh = 2, super_max = 256;
   bool frame_projected = false;  // last frame came from render_device: last_cam / last_prm describe its projection
   GsbCamera last_cam{};
   GsbParams last_prm{};
@@ -103,14 +148,14 @@ struct GsbContext {
   GsbCamera saved_cam{};
   GsbParams saved_prm{};
   uint64_t scene_gen = 0, saved_gen = 0;
-  uint32_t* pinned = nullptr;  // mailbox written by tile_stats_kernel: [0]=M, [2..3]=K, [4]=frame sequence number
+  int64_t frame_id = 0, saved_frame_id = 0;
+  uint32_t* pinned = nullptr;      // mailbox written by tile_stats_kernel: {M, V, K lo, K hi, seq, abort, Ks lo, Ks hi}
   uint32_t* pinned_dev = nullptr;  // device alias of the mailbox
   uint32_t seq = 0;
   cudaStream_t aux = nullptr;   // side stream for work that is off the critical path (tile stats)
   cudaEvent_t ev_fork = nullptr, ev_stats = nullptr;
   // asynchronous image egress: two device staging images, a copy stream, one event per staging image
   cudaStream_t copy = nullptr;
-  DevBuf host_stage[2];
   cudaEvent_t ev_rendered = nullptr, ev_copied[2] = {nullptr, nullptr};
   bool copy_pending[2] = {false, false};
   int stage_next = 0;
@@ -122,15 +167,18 @@ struct GsbContext {
   bool order_in_a = true;
   bool have_order = false;
   int64_t frame_rows = 0;  // rows of the per-Gaussian arrays of the last frame (N, or M for gsb_render_image)
+  int tail_reruns = 0;     // frames whose tail had to be queued twice (a count outgrew its buffer)
   GsbFrameInfo info{};
-  cudaEvent_t ev[GSB_NUM_STAGES + 5]{};
-  int mark_stage[GSB_NUM_STAGES + 5]{};
+  cudaEvent_t ev[GSB_NUM_STAGES + 9]{};
+  int mark_stage[GSB_NUM_STAGES + 9]{};
   int n_marks = 0;
   float stage_ms[GSB_NUM_STAGES]{};
   bool have_times = false;
 };
 
 namespace {
+
+constexpr int kMaxMarks = GSB_NUM_STAGES + 8;
 
 // chronological list of (stage, event): a stage's time is its event minus the previous one in the list
 struct StageTimer {
@@ -142,7 +190,7 @@ struct StageTimer {
     if (on) cudaEventRecord(c->ev[0], st);
   }
   void mark(int stage) {
-    if (!on || c->n_marks >= GSB_NUM_STAGES + 4) return;
+    if (!on || c->n_marks >= kMaxMarks) return;
     ++c->n_marks;
     c->mark_stage[c->n_marks] = stage;
     cudaEventRecord(c->ev[c->n_marks], st);
@@ -155,50 +203,84 @@ int check_params(const GsbCamera* cam, const GsbParams* prm) {
   if (cam->width <= 0 || cam->height <= 0) return GSB_E_INVALID_ARG;
   if (cam->width > 65535 * kTile || cam->height > 65535 * kTile) return GSB_E_UNSUPPORTED;
   if (prm->semantics != GSB_SEM_REF_CPU && prm->semantics != GSB_SEM_REF_CU) return GSB_E_INVALID_ARG;
-  if (prm->sort_mode < GSB_SORT_AUTO || prm->sort_mode > GSB_SORT_BINNED) return GSB_E_INVALID_ARG;
+  if (prm->sort_mode < GSB_SORT_AUTO || prm->sort_mode > GSB_SORT_SPLIT) return GSB_E_INVALID_ARG;
+  if (prm->cull_alpha != prm->cull_alpha) return GSB_E_INVALID_ARG;
   return GSB_OK;
 }
 
-// tile_stats_kernel needs only the projection's difference grid, not the depth sort: run it on the context's
+// every entry point that overwrites per-frame state starts a new frame: a frame saved for the backward pass is gone
+void begin_frame(GsbContext* c) {
+  c->have_frame = false;
+  c->frame_projected = false;
+  c->have_order = false;
+  c->have_saved = false;
+  c->have_times = false;
+  ++c->frame_id;
+  std::memset(&c->info, 0, sizeof(c->info));
+  c->info.frame_id = c->frame_id;
+}
+
+struct Counts {
+  int64_t m = 0, v = 0, k = 0, ks = 0;
+  bool abort = false;
+};
+
+// tile_stats_kernel needs only the projection's difference grids, not the depth sort: run it on the context's
 // auxiliary stream so that it overlaps the (latency-bound) depth-sort passes; the main stream joins on ev_stats.
-int launch_stats_async(GsbContext* c, FrameGeom geom, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, int* launches) {
+// `sg` with lw + lh > 0 adds the launch over the super-tile grid; the last launch decides abort and posts the mailbox.
+int launch_stats_async(GsbContext* c, FrameGeom geom, SuperGeom sg, bool split, uint32_t* ctl, const CtlLayout& L,
+                       uint64_t cap_k, uint64_t cap_ks, cudaStream_t st, int* launches) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
   GSB_TRY(c->ranges.ensure((size_t)(tiles > 0 ? tiles : 1) * 8));
+  if (tiles <= 0) return GSB_OK;
+  const bool two_level = split && sg.lw + sg.lh > 0;
+  if (two_level) GSB_TRY(c->ranges_s.ensure((size_t)sg.nx * sg.ny * 8));
   GSB_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
   GSB_CUDA_TRY(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
   ++c->seq;
-  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom, ctl + L.hist + 4 * kRadix,
-                                              c->ranges.as<uint2>(), ctl + 2, ctl, c->pinned_dev, c->seq, c->aux));
-  if (tiles > 0) ++*launches;
+  uint32_t* tile_hist = ctl + L.hist + 4 * kRadix;
+  StatsPost post{0, two_level ? 0 : 1, cap_k, cap_ks, c->pinned_dev, c->seq};
+  GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid), geom.tiles_x, geom.tiles_y,
+                                              two_level ? nullptr : tile_hist, c->ranges.as<uint2>(), ctl, post, c->aux));
+  ++*launches;
+  if (two_level) {
+    post.level = 1;
+    post.enabled = 1;
+    GSB_CUDA_TRY((cudaError_t)launch_tile_stats(reinterpret_cast<int32_t*>(ctl + L.grid_s), sg.nx, sg.ny, tile_hist,
+                                                c->ranges_s.as<uint2>(), ctl, post, c->aux));
+    ++*launches;
+  }
   GSB_CUDA_TRY(cudaEventRecord(c->ev_stats, c->aux));
   return GSB_OK;
 }
 
-// Wait for tile_stats_kernel's mailbox (M, K) without draining the main stream: the depth-sort passes queued
-// behind the projection keep running while the host sizes the key buffers and queues emit / sort / composite.
-int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t st, int64_t* m, int64_t* k,
-                int64_t* v = nullptr) {
-  if (v) *v = 0;
-  if (tiles <= 0) {  // no tile grid, no tile_stats launch: plain read-back of M, K = 0
+// Pick up the counts tile_stats_kernel posted, without draining any stream.
+int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t st, Counts* out) {
+  *out = Counts{};
+  if (tiles <= 0) {  // no tile grid, no tile_stats launch: plain read-back of M
     GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, ctl, 4, cudaMemcpyDeviceToHost, st));
     GSB_CUDA_TRY(cudaStreamSynchronize(st));
-    *m = c->pinned[0]; *k = 0;
+    out->m = c->pinned[0];
     return GSB_OK;
   }
-  volatile uint32_t* box = c->pinned;
+  const uint32_t* box = c->pinned;
   const auto t0 = std::chrono::steady_clock::now();
-  for (uint64_t spins = 0; box[4] != c->seq; ++spins) {
+  // acquire: the counts below must not be read before the sequence number (weakly ordered hosts)
+  for (uint64_t spins = 0; __atomic_load_n(&box[4], __ATOMIC_ACQUIRE) != c->seq; ++spins) {
     if ((spins & 0x3FFF) == 0x3FFF) {
       cudaError_t q = cudaStreamQuery(c->aux);
       if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
-      if (q == cudaSuccess && box[4] != c->seq) return GSB_E_INTERNAL;  // kernel finished, mailbox never written
+      if (q == cudaSuccess && __atomic_load_n(&box[4], __ATOMIC_ACQUIRE) != c->seq) return GSB_E_INTERNAL;  // kernel finished, mailbox never written
       // a stream that never runs (e.g. waiting on an event nobody records) must not hang the caller for ever
       if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) return GSB_E_INTERNAL;
     }
   }
-  *m = box[0];
-  *k = (int64_t)(((uint64_t)box[3] << 32) | box[2]);
-  if (v) *v = box[1];
+  auto ld = [&](int i) { return (uint64_t)__atomic_load_n(&box[i], __ATOMIC_RELAXED); };
+  out->m = (int64_t)ld(0);
+  out->v = (int64_t)ld(1);
+  out->k = (int64_t)((ld(3) << 32) | ld(2));
+  out->abort = ld(5) != 0;
+  out->ks = (int64_t)((ld(7) << 32) | ld(6));
   return GSB_OK;
 }
 
@@ -221,113 +303,158 @@ int depth_sort(GsbContext* c, int64_t n, const uint32_t* hist, uint32_t* control
   return GSB_OK;
 }
 
-// everything after the per-Gaussian records exist: tile stats -> scan -> K -> emit -> sort.
-// `n_rows` per-Gaussian rows; `perm` optional emission order; `low_bits_sorted`: emission order already
-// sorts the low key word (SPLIT mode / pre-sorted rows), so only the tile digits need radix passes.
-// `rows_with_tiles`: upper bound of the emission positions that emit anything when the HOST knows one
-// (pre-sorted rows: M), -1 when the projection counted it (V, read from the mailbox).
-// With low_bits_sorted the keys shrink to 32 bits -- tile << rank_bits | emission position -- whenever
-// ceil(log2 tiles) + ceil(log2 V) <= 32 (config 3: 13 + 19); the last radix pass then writes perm[position].
-int bin_and_sort(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool low_bits_sorted, int64_t rows_with_tiles,
-                 FrameGeom geom, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches) {
+// ---- FULL mode: scan (index order) -> K to the host -> emit -> 64-bit sort.  The host needs K to size the grids,
+// so this path (the literal north-star pipeline, kept as the cross-check of SPLIT) waits for the mailbox mid-frame.
+int bin_full(GsbContext* c, int64_t n_rows, FrameGeom geom, uint32_t* ctl, const CtlLayout& L, cudaStream_t st,
+             StageTimer& tm, int* launches) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
   GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
-  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), perm, n_rows, c->offsets.as<uint32_t>(), ctl + L.scan, st));
+  GSB_CUDA_TRY((cudaError_t)launch_scan(c->count.as<uint32_t>(), nullptr, n_rows, c->offsets.as<uint32_t>(), ctl + L.scan, st));
   if (n_rows > 0) ++*launches;
   tm.mark(GSB_STAGE_SCAN);
-  // tile stats were launched on the auxiliary stream right after the projection (they do not depend on the
-  // depth sort) and post M and K to the host mailbox; pick them up without draining the main stream
-  int64_t m = 0, k = 0, v = 0;
-  GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k, &v));
-  GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // ranges / tile histograms are inputs of what follows
-  if (k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
-  c->info.m_in_view = m;
-  c->info.k_instances = k;
-  if (rows_with_tiles >= 0) v = rows_with_tiles;
-
+  Counts cn;
+  GSB_TRY(wait_counts(c, tiles, ctl, st, &cn));
+  if (tiles > 0) GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // tile histograms are inputs of the sort
+  if (cn.k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
+  c->info.m_in_view = cn.m;
+  c->info.k_instances = cn.k;
+  c->info.k_sorted = cn.k;
+  const int64_t k = cn.k;
   GSB_TRY(c->keys_a.ensure((size_t)k * 8 + 8));
   GSB_TRY(c->keys_b.ensure((size_t)k * 8 + 8));
   GSB_TRY(c->vals_a.ensure((size_t)k * 4 + 4));
   GSB_TRY(c->vals_b.ensure((size_t)k * 4 + 4));
-
   const int tile_bits = ceil_log2(tiles);
-  const int rank_bits = ceil_log2(v);
-  const bool keys32 = low_bits_sorted && c->allow_keys32 && tile_bits + rank_bits <= 32;
-  const uint32_t* hist = ctl + L.hist + (low_bits_sorted ? 4 * kRadix : 0);
+  SortPlan plan = make_sort_plan<uint64_t>(k, 0, 32 + tile_bits);
+  GSB_TRY(c->control2.ensure(plan.control_words * 4));
+  GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+  GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), nullptr, ctl + kCtlK, n_rows, k,
+                                        c->depth_key.as<uint32_t>(), c->rect.as<ushort4>(), geom.tiles_x,
+                                        c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
+  if (n_rows > 0 && k > 0) ++*launches;
+  tm.mark(GSB_STAGE_EMIT);
   bool in_a = true;
-  int passes = 0;
-  if (keys32) {
-    SortPlan plan = make_sort_plan<uint32_t>(k, rank_bits, rank_bits + tile_bits);
-    plan.keys_only = 1;
-    plan.low_bits = rank_bits;
-    plan.gather_table = perm;  // nullptr (pre-sorted rows): the position IS the row
-    GSB_TRY(c->control2.ensure(plan.control_words * 4));
-    GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
-    GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 2, n_rows, k, c->depth_key.as<uint32_t>(),
-                                          c->rect.as<ushort4>(), geom.tiles_x, true, rank_bits,
-                                          c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
-    if (n_rows > 0 && k > 0) ++*launches;
-    tm.mark(GSB_STAGE_EMIT);
-    GSB_CUDA_TRY((cudaError_t)launch_sort<uint32_t>(plan, c->keys_a.as<uint32_t>(), nullptr, c->keys_a.as<uint32_t>(),
-                                                    c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(),
-                                                    c->vals_b.as<uint32_t>(), hist, c->control2.as<uint32_t>(), &in_a,
-                                                    launches, st));
-    passes = plan.passes;
-  } else {
-    SortPlan plan = low_bits_sorted ? make_sort_plan<uint64_t>(k, 32, 32 + tile_bits)
-                                    : make_sort_plan<uint64_t>(k, 0, 32 + tile_bits);
-    GSB_TRY(c->control2.ensure(plan.control_words * 4));
-    GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
-    plan.keys_only = low_bits_sorted ? 1 : 0;
-    GSB_CUDA_TRY((cudaError_t)launch_emit(c->offsets.as<uint32_t>(), perm, ctl + 2, n_rows, k, c->depth_key.as<uint32_t>(),
-                                          c->rect.as<ushort4>(), geom.tiles_x, /*combined=*/low_bits_sorted, 0,
-                                          c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), st));
-    if (n_rows > 0 && k > 0) ++*launches;
-    tm.mark(GSB_STAGE_EMIT);
-    GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
-                                                    c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
-                                                    c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(), hist,
-                                                    c->control2.as<uint32_t>(), &in_a, launches, st));
-    passes = plan.passes;
-  }
-  c->keys_materialized = !low_bits_sorted;
+  GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
+                                                  c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(),
+                                                  c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(), ctl + L.hist,
+                                                  c->control2.as<uint32_t>(), &in_a, launches, st));
+  c->keys_materialized = true;
   c->sorted_in_a = in_a;
-  c->emitted_valid = (passes <= 1) && !low_bits_sorted;  // one pass: the a-buffers still hold the emitted order
-  c->info.sort_passes = (k > 0) ? passes : 0;
-  c->info.key_bits = keys32 ? 32 : 64;
+  c->emitted_valid = plan.passes <= 1;  // one pass: the a-buffers still hold the emitted order
+  c->info.sort_passes = (k > 0) ? plan.passes : 0;
+  c->info.key_bits = 64;
+  c->info.super_w = c->info.super_h = 1;
   tm.mark(GSB_STAGE_SORT);
   return GSB_OK;
 }
 
-// BINNED mode: tile stats -> K -> unordered per-tile segments (atomic cursors) -> per-tile sort by depth rank.
-int bin_by_tile(GsbContext* c, int64_t n_rows, const uint32_t* order, FrameGeom geom, uint32_t* ctl, const CtlLayout& L,
-                cudaStream_t st, StageTimer& tm, int* launches) {
-  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
-  int64_t m = 0, k = 0;
-  GSB_TRY(wait_counts(c, tiles, ctl, st, &m, &k));
-  GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // tile stats ran on the auxiliary stream
-  if (k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
-  c->info.m_in_view = m;
-  c->info.k_instances = k;
-  GSB_TRY(c->vals_a.ensure((size_t)k * 4 + 4));
-  GSB_TRY(c->keys_a.ensure((size_t)k * 4 + 4));  // scratch for tile segments longer than shared memory
-  GSB_TRY(c->keys_b.ensure((size_t)k * 4 + 4));
-  if (k > 0 && n_rows > 0) {
-    GSB_CUDA_TRY((cudaError_t)launch_emit_binned(n_rows, c->rect.as<ushort4>(), c->count.as<uint32_t>(), geom.tiles_x,
-                                                 c->ranges.as<uint2>(), ctl + L.cursor, c->vals_a.as<uint32_t>(), st));
+// ---- SPLIT mode, everything between the scan and the compositing kernel, queued from capacities.
+// Rows are in emission order (`perm`, or identity) with their depth digits already sorted; `v_limit` (optional):
+// device word holding the number of leading emission positions that touch tiles.
+struct SplitPlan {
+  SuperGeom sg;
+  bool two_level, keys32;
+  int rank_bits, sbits;
+  int64_t cap_k, cap_ks;
+};
+
+int split_capacities(GsbContext* c, int64_t n_rows, const SplitPlan& sp, int64_t need_k, int64_t need_ks) {
+  // payload: 4 B per tile instance; super-tile level: one key ping-pong + the sorted indices
+  const size_t kb = sp.keys32 ? 4 : 8;
+  if (need_k < 16 * n_rows) need_k = 16 * n_rows;  // first guess of a fresh context
+  if (!sp.two_level) need_ks = need_k;
+  else if (need_ks < 4 * n_rows) need_ks = 4 * n_rows;
+  GSB_TRY(c->vals_a.ensure((size_t)need_k * 4 + 16));
+  GSB_TRY(c->ckeys_a.ensure((size_t)need_ks * kb + 16));
+  GSB_TRY(c->ckeys_b.ensure((size_t)need_ks * kb + 16));
+  if (sp.two_level) GSB_TRY(c->cvals.ensure((size_t)need_ks * 4 + 16));
+  return GSB_OK;
+}
+
+SplitPlan make_split_plan(GsbContext* c, int64_t n_rows, FrameGeom geom, SuperGeom sg) {
+  SplitPlan sp;
+  sp.sg = sg;
+  sp.two_level = sg.lw + sg.lh > 0;
+  sp.sbits = ceil_log2((int64_t)sg.nx * sg.ny);
+  sp.rank_bits = ceil_log2(n_rows);
+  sp.keys32 = c->allow_keys32 && sp.sbits + sp.rank_bits <= 32;
+  (void)geom;
+  sp.cap_k = sp.cap_ks = 0;
+  return sp;
+}
+
+void read_capacities(GsbContext* c, SplitPlan& sp) {
+  const size_t kb = sp.keys32 ? 4 : 8;
+  const int64_t lim = ((int64_t)1 << 32) - 2;  // positions are u32
+  int64_t ck = (int64_t)((c->vals_a.cap - 16) / 4);
+  int64_t cks = (int64_t)((c->ckeys_a.cap - 16) / kb);
+  const int64_t cks_b = (int64_t)((c->ckeys_b.cap - 16) / kb);
+  if (cks_b < cks) cks = cks_b;
+  if (sp.two_level) {
+    const int64_t cv = (int64_t)((c->cvals.cap - 16) / 4);
+    if (cv < cks) cks = cv;
+  } else {
+    if (ck < cks) cks = ck; else ck = cks;
+  }
+  sp.cap_k = ck < lim ? ck : lim;
+  sp.cap_ks = cks < lim ? cks : lim;
+}
+
+int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const uint32_t* v_limit, FrameGeom geom,
+                     const SplitPlan& sp, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm,
+                     int* launches) {
+  const uint32_t* abort = ctl + kCtlAbort;
+  const uint32_t* hist = ctl + L.hist + 4 * kRadix;
+  uint32_t* out_vals = sp.two_level ? c->cvals.as<uint32_t>() : c->vals_a.as<uint32_t>();
+  bool in_a = true;
+  int passes = 0;
+  if (sp.keys32) {
+    SortPlan plan = make_sort_plan<uint32_t>(sp.cap_ks, sp.rank_bits, sp.rank_bits + sp.sbits);
+    plan.keys_only = 1;
+    plan.low_bits = sp.rank_bits;
+    plan.gather_table = perm;  // nullptr (pre-sorted rows): the position IS the row
+    plan.n_dev = ctl + kCtlKs;
+    plan.abort = abort;
+    GSB_TRY(c->control2.ensure(plan.control_words * 4));
+    GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+    GSB_CUDA_TRY((cudaError_t)launch_emit_coarse(c->offsets.as<uint32_t>(), perm, ctl + kCtlKs, n_rows, v_limit, abort,
+                                                 sp.cap_ks, c->rect.as<ushort4>(), sp.sg, sp.rank_bits, c->ckeys_a.p, st));
     ++*launches;
     tm.mark(GSB_STAGE_EMIT);
-    const int rank_bits = ceil_log2(n_rows);
-    GSB_CUDA_TRY((cudaError_t)launch_tile_sort(c->ranges.as<uint2>(), (int)tiles, c->rank.as<uint32_t>(), order,
-                                               c->vals_a.as<uint32_t>(), rank_bits, c->keys_a.as<uint32_t>(),
-                                               c->keys_b.as<uint32_t>(), st));
+    GSB_CUDA_TRY((cudaError_t)launch_sort<uint32_t>(plan, c->ckeys_a.as<uint32_t>(), nullptr, c->ckeys_a.as<uint32_t>(),
+                                                    out_vals, c->ckeys_b.as<uint32_t>(), out_vals, hist,
+                                                    c->control2.as<uint32_t>(), &in_a, launches, st));
+    passes = plan.passes;
+  } else {
+    SortPlan plan = make_sort_plan<uint64_t>(sp.cap_ks, 32, 32 + sp.sbits);
+    plan.keys_only = 1;
+    plan.n_dev = ctl + kCtlKs;
+    plan.abort = abort;
+    GSB_TRY(c->control2.ensure(plan.control_words * 4));
+    GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
+    GSB_CUDA_TRY((cudaError_t)launch_emit_coarse(c->offsets.as<uint32_t>(), perm, ctl + kCtlKs, n_rows, v_limit, abort,
+                                                 sp.cap_ks, c->rect.as<ushort4>(), sp.sg, 0, c->ckeys_a.p, st));
     ++*launches;
-    c->info.sort_passes = (rank_bits + 7) / 8;
-    tm.mark(GSB_STAGE_SORT);
+    tm.mark(GSB_STAGE_EMIT);
+    GSB_CUDA_TRY((cudaError_t)launch_sort<uint64_t>(plan, c->ckeys_a.as<uint64_t>(), nullptr, c->ckeys_a.as<uint64_t>(),
+                                                    out_vals, c->ckeys_b.as<uint64_t>(), out_vals, hist,
+                                                    c->control2.as<uint32_t>(), &in_a, launches, st));
+    passes = plan.passes;
   }
+  tm.mark(GSB_STAGE_SORT);
+  if (sp.two_level) {
+    GSB_CUDA_TRY((cudaError_t)launch_expand(c->ranges_s.as<uint2>(), c->cvals.as<uint32_t>(), c->rect.as<ushort4>(),
+                                            c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), geom, sp.sg, abort, st));
+    ++*launches;
+    tm.mark(GSB_STAGE_EXPAND);
+  }
+  c->keys_materialized = false;
   c->sorted_in_a = true;
   c->emitted_valid = false;
-  c->keys_materialized = false;
+  c->info.sort_passes = passes;
+  c->info.key_bits = sp.keys32 ? 32 : 64;
+  c->info.super_w = 1 << sp.sg.lw;
+  c->info.super_h = 1 << sp.sg.lh;
   return GSB_OK;
 }
 
@@ -343,6 +470,71 @@ void finish_times(GsbContext* c, cudaStream_t st, bool on) {
   c->have_times = true;
 }
 
+// What follows the per-Gaussian records in SPLIT mode, shared by gsb_render (projected rows, depth order in `perm`)
+// and gsb_render_image (the caller's pre-sorted rows): scan -> [emit, sort, expand, composite] queued from
+// capacities -> counts from the mailbox -> on overflow grow and queue the bracketed tail once more.
+template <typename CompositeFn>
+int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sorted_by_visibility, FrameGeom geom,
+              SuperGeom sg, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches,
+              CompositeFn&& queue_composite) {
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  if (tiles <= 0 || n_rows <= 0) {  // nothing to bin; the compositing launcher handles an empty grid itself
+    Counts cn;
+    if (n_rows > 0) GSB_TRY(wait_counts(c, 0, ctl, st, &cn));
+    c->info.m_in_view = cn.m;
+    c->info.super_w = c->info.super_h = 1;
+    if (tiles > 0) {  // no rows: every range is (0,0)
+      GSB_TRY(c->ranges.ensure((size_t)tiles * 8));
+      GSB_CUDA_TRY(cudaMemsetAsync(c->ranges.p, 0, (size_t)tiles * 8, st));
+      GSB_TRY(c->vals_a.ensure(16));
+    }
+    c->keys_materialized = false;
+    c->sorted_in_a = true;
+    c->emitted_valid = false;
+    return queue_composite(nullptr);
+  }
+  const uint32_t* v_limit = rows_sorted_by_visibility ? ctl + kCtlVisible : nullptr;
+  GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
+  GSB_CUDA_TRY((cudaError_t)launch_scan_coarse(c->rect.as<ushort4>(), sg, perm, n_rows, v_limit, c->offsets.as<uint32_t>(),
+                                               ctl + L.scan, st));
+  ++*launches;
+  tm.mark(GSB_STAGE_SCAN);
+  GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // ranges / super-tile histograms are inputs of what follows
+  SplitPlan sp = make_split_plan(c, n_rows, geom, sg);
+  read_capacities(c, sp);  // the capacities tile_stats_kernel was given (launch_stats_async ran with the same values)
+  GSB_TRY(queue_split_tail(c, n_rows, perm, v_limit, geom, sp, ctl, L, st, tm, launches));
+  GSB_TRY(queue_composite(ctl + kCtlAbort));
+  Counts cn;
+  GSB_TRY(wait_counts(c, tiles, ctl, st, &cn));
+  if (cn.k >= ((int64_t)1 << 32) - 1 || cn.ks >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // positions are u32
+  c->info.m_in_view = cn.m;
+  c->info.k_instances = cn.k;
+  c->info.k_sorted = cn.ks;
+  if (cn.abort) {
+    // a count outgrew its buffer: none of the tail kernels touched anything.  Grow (cudaFree drains the device),
+    // clear the flag and queue the tail once more; the projection, depth order, ranges and offsets stand.
+    ++c->tail_reruns;
+    GSB_TRY(split_capacities(c, n_rows, sp, cn.k, cn.ks));
+    read_capacities(c, sp);
+    if (cn.k > sp.cap_k || cn.ks > sp.cap_ks) return GSB_E_INTERNAL;
+    GSB_CUDA_TRY(cudaMemsetAsync(ctl + kCtlAbort, 0, 4, st));
+    GSB_TRY(queue_split_tail(c, n_rows, perm, v_limit, geom, sp, ctl, L, st, tm, launches));
+    GSB_TRY(queue_composite(ctl + kCtlAbort));
+  }
+  return GSB_OK;
+}
+
+// capacities the stats kernel is told for this frame (must equal what run_split reads back: both derive them from
+// the same buffers, and nothing reallocates in between)
+int prepare_split(GsbContext* c, int64_t n_rows, FrameGeom geom, SuperGeom sg, uint64_t* cap_k, uint64_t* cap_ks) {
+  SplitPlan sp = make_split_plan(c, n_rows, geom, sg);
+  GSB_TRY(split_capacities(c, n_rows, sp, 0, 0));  // no-op once the buffers exist
+  read_capacities(c, sp);
+  *cap_k = (uint64_t)sp.cap_k;
+  *cap_ks = (uint64_t)sp.cap_ks;
+  return GSB_OK;
+}
+
 // projection + binning + sort + compositing into a DEVICE image buffer
 int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float* dev_image, cudaStream_t st) {
   GSB_TRY(check_params(cam, prm));
@@ -353,16 +545,12 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   const int64_t n = c->n;
   FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
                  tile_grid_dim(cam->height, kTile, prm->full_cover)};
-  // AUTO = SPLIT, the fastest measured (config 3: tile sort 183 us vs 562 us FULL; BINNED spends 140 us in the
-  // atomic emit and 370 us in the per-tile sort, profiles/r1_summary.md)
-  const int mode = prm->sort_mode == GSB_SORT_AUTO ? GSB_SORT_SPLIT : prm->sort_mode;
-  const bool split = mode != GSB_SORT_FULL;  // SPLIT and BINNED both sort the depth keys per Gaussian first
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  const bool split = prm->sort_mode != GSB_SORT_FULL;  // AUTO = SPLIT
+  const SuperGeom sg = split ? choose_super(geom, c->super_lw, c->super_lh, c->super_max) : SuperGeom{0, 0, geom.tiles_x, geom.tiles_y};
+  const bool two_level = split && sg.lw + sg.lh > 0;
   int launches = 0;
-  c->have_frame = false;
-  c->frame_projected = false;
-  c->have_order = false;
-  c->have_saved = false;
-  std::memset(&c->info, 0, sizeof(c->info));
+  begin_frame(c);
   c->info.n = n; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
   StageTimer tm{c, st, prm->collect_stage_times != 0};
 
@@ -372,8 +560,10 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   GSB_TRY(c->rect.ensure(rows * 8));
   GSB_TRY(c->count.ensure(rows * 4));
   SortPlan dplan = make_sort_plan<uint32_t>(n, 0, 32);
-  const CtlLayout L = ctl_layout(geom, n, split ? dplan.control_words : 0);
+  const CtlLayout L = ctl_layout(geom, sg, n, split ? dplan.control_words : 0);
   GSB_TRY(c->control.ensure(L.total * 4));
+  uint64_t cap_k = ~0ull, cap_ks = ~0ull;  // FULL: the host sizes everything after it has seen K
+  if (split && n > 0 && tiles > 0) GSB_TRY(prepare_split(c, n, geom, sg, &cap_k, &cap_ks));
   GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* ctl = c->control.as<uint32_t>();
 
@@ -381,32 +571,12 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, *cam, *prm, geom, c->depth_key.as<uint32_t>(),
                                            c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), ctl,
                                            ctl + L.hist, /*hist_weighted=*/split ? 0 : 1,
-                                           reinterpret_cast<int32_t*>(ctl + L.grid), nullptr, st));
+                                           reinterpret_cast<int32_t*>(ctl + L.grid),
+                                           two_level ? reinterpret_cast<int32_t*>(ctl + L.grid_s) : nullptr, sg, nullptr, st));
   if (n > 0) ++launches;
   tm.mark(GSB_STAGE_PROJECT);
-  GSB_TRY(launch_stats_async(c, geom, ctl, L, st, &launches));
-  const uint32_t* perm = nullptr;
-  if (split && n > 0) {
-    int dp = 0;
-    GSB_TRY(depth_sort(c, n, ctl + L.hist, ctl + L.dsort, st, &launches, &dp));
-    c->info.depth_passes = dp;
-    perm = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
-    if (mode == GSB_SORT_BINNED) {
-      GSB_TRY(c->rank.ensure(rows * 4));
-      GSB_CUDA_TRY((cudaError_t)launch_invert_perm(perm, n, c->rank.as<uint32_t>(), st));
-      ++launches;
-    }
-    tm.mark(GSB_STAGE_DEPTH_SORT);
-  }
-  if (mode == GSB_SORT_BINNED) {
-    GSB_TRY(bin_by_tile(c, n, perm, geom, ctl, L, st, tm, &launches));
-  } else {
-    GSB_TRY(bin_and_sort(c, n, perm, split, /*rows_with_tiles=*/-1, geom, ctl, L, st, tm, &launches));
-  }
+  if (n > 0) GSB_TRY(launch_stats_async(c, geom, sg, split, ctl, L, cap_k, cap_ks, st, &launches));
 
-  if (!prm->full_cover)  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
-    GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
-  const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
   float* aux_t = nullptr;
   uint32_t* aux_n = nullptr;
   if (prm->save_for_backward) {
@@ -415,12 +585,53 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
     GSB_TRY(c->aux_n.ensure(px * 4));
     aux_t = c->aux_t.as<float>();
     aux_n = c->aux_n.as<uint32_t>();
-    if (!prm->full_cover) GSB_CUDA_TRY(cudaMemsetAsync(aux_n, 0, px * 4, st));  // pixels outside the grid: nothing blended
   }
-  GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, *prm,
-                                             aux_t, aux_n, st));
-  if (geom.tiles_x * geom.tiles_y > 0) ++launches;
-  tm.mark(GSB_STAGE_COMPOSITE);
+  auto queue_composite = [&](const uint32_t* abort) -> int {
+    if (!prm->full_cover) {  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
+      GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
+      if (aux_n) GSB_CUDA_TRY(cudaMemsetAsync(aux_n, 0, (size_t)cam->width * cam->height * 4, st));  // nothing blended there
+    }
+    GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), c->rec.as<float4>(),
+                                               dev_image, geom, *prm, aux_t, aux_n, abort, st));
+    if (tiles > 0) ++launches;
+    tm.mark(GSB_STAGE_COMPOSITE);
+    return GSB_OK;
+  };
+
+  if (split) {
+    const uint32_t* perm = nullptr;
+    if (n > 0) {
+      int dp = 0;
+      GSB_TRY(depth_sort(c, n, ctl + L.hist, ctl + L.dsort, st, &launches, &dp));
+      c->info.depth_passes = dp;
+      perm = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
+      tm.mark(GSB_STAGE_DEPTH_SORT);
+    }
+    GSB_TRY(run_split(c, n, perm, /*rows_sorted_by_visibility=*/true, geom, sg, ctl, L, st, tm, &launches, queue_composite));
+  } else {
+    if (n > 0 && tiles > 0) {
+      GSB_TRY(bin_full(c, n, geom, ctl, L, st, tm, &launches));
+    } else {
+      Counts cn;
+      if (n > 0) GSB_TRY(wait_counts(c, 0, ctl, st, &cn));
+      c->info.m_in_view = cn.m;
+      if (tiles > 0) {
+        GSB_TRY(c->ranges.ensure((size_t)tiles * 8));
+        GSB_CUDA_TRY(cudaMemsetAsync(c->ranges.p, 0, (size_t)tiles * 8, st));
+        GSB_TRY(c->vals_a.ensure(16));
+      }
+      c->sorted_in_a = true;
+      c->keys_materialized = false;
+      c->emitted_valid = false;
+    }
+    if (!c->sorted_in_a) {  // the compositing launcher above reads vals_a: an odd pass count left the order in vals_b
+      std::swap(c->vals_a.p, c->vals_b.p); std::swap(c->vals_a.cap, c->vals_b.cap);
+      std::swap(c->keys_a.p, c->keys_b.p); std::swap(c->keys_a.cap, c->keys_b.cap);
+      c->sorted_in_a = true;
+      c->emitted_valid = false;
+    }
+    GSB_TRY(queue_composite(nullptr));
+  }
   c->info.kernel_launches = launches;
   c->frame_rows = n;
   c->have_frame = true;
@@ -432,6 +643,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
     c->saved_cam = *cam;
     c->saved_prm = *prm;
     c->saved_gen = c->scene_gen;
+    c->saved_frame_id = c->frame_id;
   }
   finish_times(c, st, tm.on);
   return GSB_OK;
@@ -454,7 +666,7 @@ const char* gsb_error_string(int s) {
     case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case GSB_E_ALLOC: return "device memory allocation failed";
     case GSB_E_INTERNAL: return "internal error (device-side consistency check failed, or the stream made no progress)";
-    case GSB_E_NO_SAVED: return "no saved frame for the backward pass (render with save_for_backward = 1 and the same camera / params first)";
+    case GSB_E_NO_SAVED: return "no saved frame for the backward pass (render with save_for_backward = 1 and the same camera / params first; any other render, preprocess or upload on the context discards it)";
     default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown error";
   }
 }
@@ -475,6 +687,7 @@ void gsb_default_params(GsbParams* p) {
   p->collect_stage_times = 0;
   p->async_host_copy = 0;
   p->save_for_backward = 0;
+  p->cull_alpha = 9.31322574615478515625e-10f;  // 2^-30
 }
 
 int gsb_create(GsbContext** out, int device) {
@@ -492,8 +705,17 @@ int gsb_create(GsbContext** out, int device) {
     set_sort_items(e ? std::atoi(e) : 16);
     e = std::getenv("GSB_FORCE_WIDE_STATUS");             // 1: 64-bit look-back words even below 2^30 keys
     set_force_wide_status(e ? std::atoi(e) : 0);
-    e = std::getenv("GSB_KEYS32");                        // 0: never use the 32-bit tile keys of SPLIT mode
+    e = std::getenv("GSB_KEYS32");                        // 0: never use 32-bit keys for the super-tile passes
     c->allow_keys32 = !e || std::atoi(e) != 0;
+    e = std::getenv("GSB_SUPER");                         // "lw,lh": log2 tiles per super-tile; "0,0": one level
+    if (e) {
+      int lw = 3, lh = 2;
+      if (std::sscanf(e, "%d,%d", &lw, &lh) == 2 && lw >= 0 && lh >= 0 && lw <= 8 && lh <= 8 && (lw + lh == 0 || lw + lh >= 4)) {
+        c->super_lw = lw; c->super_lh = lh;
+      }
+    }
+    e = std::getenv("GSB_SUPER_MAX");                     // most super-tiles per frame (256 = one radix pass)
+    if (e && std::atoi(e) >= 1) c->super_max = std::atoi(e);
   }
   if (cudaHostAlloc((void**)&c->pinned, 64, cudaHostAllocMapped) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
   std::memset(c->pinned, 0, 64);
@@ -518,22 +740,16 @@ void gsb_destroy(GsbContext* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  DevBuf* bufs[] = {&c->planes, &c->staging, &c->depth_key, &c->rec, &c->rect, &c->count, &c->offsets, &c->bbox,
-                    &c->dbg_cov2d, &c->dbg_conic, &c->dbg_bbox, &c->ord_keys_a, &c->ord_keys_b, &c->ord_vals_a,
-                    &c->ord_vals_b, &c->rank, &c->keys_a, &c->keys_b, &c->vals_a, &c->vals_b, &c->ranges, &c->control,
-                    &c->control2, &c->image, &c->image2, &c->scratch};
-  for (DevBuf* b : bufs) b->release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->aux) cudaStreamDestroy(c->aux);
   if (c->copy) cudaStreamDestroy(c->copy);
   if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
   for (auto& e : c->ev_copied) if (e) cudaEventDestroy(e);
-  c->host_stage[0].release(); c->host_stage[1].release();
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_stats) cudaEventDestroy(c->ev_stats);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
-  delete c;
+  delete c;  // every DevBuf member frees its device memory in its destructor
 }
 
 int gsb_upload(GsbContext* c, int64_t n, const float* xyz, const float* scales, const float* quats,
@@ -611,12 +827,15 @@ int gsb_render(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, float*
   return GSB_OK;
 }
 
-int gsb_render_backward(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, const float* grad_image,
-                        float* grad_points, float* grad_scales, float* grad_quats, float* grad_colors,
-                        float* grad_opacity, void* stream) {
+int gsb_render_backward(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, int64_t frame_id,
+                        const float* grad_image, float* grad_points, float* grad_scales, float* grad_quats,
+                        float* grad_colors, float* grad_opacity, void* stream) {
   if (!c || !grad_image) return GSB_E_INVALID_ARG;
   GSB_TRY(check_params(cam, prm));
-  if (!c->have_frame || !c->have_saved || c->saved_gen != c->scene_gen ||
+  // the saved state IS the context's per-frame scratch: valid only while the saved frame is still the last thing
+  // that wrote it (begin_frame / gsb_upload / the debug projection clear have_saved)
+  if (!c->have_frame || !c->have_saved || c->saved_gen != c->scene_gen || c->saved_frame_id != c->frame_id ||
+      (frame_id != 0 && frame_id != c->saved_frame_id) ||
       std::memcmp(&c->saved_cam, cam, sizeof(GsbCamera)) != 0 || std::memcmp(&c->saved_prm, prm, sizeof(GsbParams)) != 0)
     return GSB_E_NO_SAVED;
   cudaStream_t st = (cudaStream_t)stream;
@@ -683,8 +902,27 @@ int gsb_render_u8(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, uin
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t elems = (int64_t)cam->width * cam->height * 3;
   GSB_TRY(c->image.ensure((size_t)elems * sizeof(float)));
+  if (is_device_pointer(out)) {
+    GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
+    return launch_to_u8(c->image.as<float>(), out, elems, st);
+  }
+  if (prm->async_host_copy) {
+    // same double-buffered egress as gsb_render, a quarter of the bytes: the conversion runs on the render stream,
+    // the copy on the copy stream
+    const int b = c->stage_next;
+    c->stage_next ^= 1;
+    GSB_TRY(c->host_stage[b].ensure((size_t)elems));
+    if (c->copy_pending[b]) GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copied[b], 0));
+    GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
+    GSB_CUDA_TRY((cudaError_t)launch_to_u8(c->image.as<float>(), c->host_stage[b].as<uint8_t>(), elems, st));
+    GSB_CUDA_TRY(cudaEventRecord(c->ev_rendered, st));
+    GSB_CUDA_TRY(cudaStreamWaitEvent(c->copy, c->ev_rendered, 0));
+    GSB_CUDA_TRY(cudaMemcpyAsync(out, c->host_stage[b].p, (size_t)elems, cudaMemcpyDeviceToHost, c->copy));
+    GSB_CUDA_TRY(cudaEventRecord(c->ev_copied[b], c->copy));
+    c->copy_pending[b] = true;
+    return GSB_OK;
+  }
   GSB_TRY(render_device(c, cam, prm, c->image.as<float>(), st));
-  if (is_device_pointer(out)) return launch_to_u8(c->image.as<float>(), out, elems, st);
   GSB_TRY(c->image2.ensure((size_t)elems));
   GSB_CUDA_TRY((cudaError_t)launch_to_u8(c->image.as<float>(), c->image2.as<uint8_t>(), elems, st));
   GSB_CUDA_TRY(cudaMemcpyAsync(out, c->image2.p, (size_t)elems, cudaMemcpyDeviceToHost, st));
@@ -701,12 +939,12 @@ int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, in
   cudaStream_t st = (cudaStream_t)stream;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   const int64_t n = c->n;
-  c->have_frame = false;
-  c->frame_projected = false;
+  begin_frame(c);  // overwrites the per-frame records: a frame saved for the backward pass is gone
   if (m_out) *m_out = 0;
   if (n == 0) return GSB_OK;
   FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
                  tile_grid_dim(cam->height, kTile, prm->full_cover)};
+  const SuperGeom sg{0, 0, geom.tiles_x, geom.tiles_y};
   GSB_TRY(c->depth_key.ensure((size_t)n * 4));
   GSB_TRY(c->rec.ensure((size_t)n * 48));
   GSB_TRY(c->rect.ensure((size_t)n * 8));
@@ -715,7 +953,7 @@ int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, in
   GSB_TRY(c->dbg_conic.ensure((size_t)n * 16));
   GSB_TRY(c->dbg_bbox.ensure((size_t)n * 16));
   SortPlan dplan = make_sort_plan<uint32_t>(n, 0, 32);
-  const CtlLayout L = ctl_layout(geom, n, dplan.control_words);
+  const CtlLayout L = ctl_layout(geom, sg, n, dplan.control_words);
   GSB_TRY(c->control.ensure(L.total * 4));
   GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* hdr = c->control.as<uint32_t>();
@@ -723,12 +961,12 @@ int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, in
   GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, *cam, *prm, geom, c->depth_key.as<uint32_t>(),
                                            c->rec.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(), hdr,
                                            hdr + L.hist, /*hist_weighted=*/0, reinterpret_cast<int32_t*>(hdr + L.grid),
-                                           &dbg, st));
+                                           nullptr, sg, &dbg, st));
   int launches = 1, dp = 0;
   GSB_TRY(depth_sort(c, n, hdr + L.hist, hdr + L.dsort, st, &launches, &dp));
-  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned, hdr, 4, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaMemcpyAsync(c->pinned + 8, hdr, 4, cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
-  const int64_t m = c->pinned[0];
+  const int64_t m = c->pinned[8];
   if (m_out) *m_out = m;
   if (m == 0) return GSB_OK;
   // gather into one staging block, then copy each requested field out (device or host destination)
@@ -771,10 +1009,10 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   const bool cu = prm.semantics == GSB_SEM_REF_CU;
   const int cover = cu ? 1 : prm.full_cover;  // render.cu covers every pixel (:119-124)
   FrameGeom geom{W, H, tile_grid_dim(W, kTile, cover), tile_grid_dim(H, kTile, cover)};
-  c->have_frame = false;
-  c->frame_projected = false;
-  c->have_order = false;
-  std::memset(&c->info, 0, sizeof(c->info));
+  const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
+  const SuperGeom sg = choose_super(geom, c->super_lw, c->super_lh, c->super_max);
+  const bool two_level = sg.lw + sg.lh > 0;
+  begin_frame(c);  // overwrites rec / ranges / payload with M-row data: a frame saved for the backward pass is gone
   c->info.n = m; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
   StageTimer tm{c, st, prm.collect_stage_times != 0};
   int launches = 0;
@@ -801,34 +1039,40 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   GSB_TRY(c->rect.ensure(rows * 8));
   GSB_TRY(c->count.ensure(rows * 4));
   GSB_TRY(c->bbox.ensure(rows * 16));
-  const CtlLayout L = ctl_layout(geom, m, 0);
+  const CtlLayout L = ctl_layout(geom, sg, m, 0);
   GSB_TRY(c->control.ensure(L.total * 4));
+  uint64_t cap_k = ~0ull, cap_ks = ~0ull;
+  if (m > 0 && tiles > 0) GSB_TRY(prepare_split(c, m, geom, sg, &cap_k, &cap_ks));
   GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* hdr = c->control.as<uint32_t>();
   tm.start();
   GSB_CUDA_TRY((cudaError_t)launch_ingest_preprocessed(m, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], geom,
                                                        prm, c->depth_key.as<uint32_t>(), c->rec.as<float4>(),
                                                        c->bbox.as<float4>(), c->rect.as<ushort4>(), c->count.as<uint32_t>(),
-                                                       reinterpret_cast<int32_t*>(hdr + L.grid), st));
+                                                       reinterpret_cast<int32_t*>(hdr + L.grid),
+                                                       two_level ? reinterpret_cast<int32_t*>(hdr + L.grid_s) : nullptr, sg, st));
   if (m > 0) ++launches;
   tm.mark(GSB_STAGE_PROJECT);
-  GSB_TRY(launch_stats_async(c, geom, hdr, L, st, &launches));
-  GSB_TRY(bin_and_sort(c, m, nullptr, /*low_bits_sorted=*/true, /*rows_with_tiles=*/m, geom, hdr, L, st, tm, &launches));
-  c->info.m_in_view = m;
+  if (m > 0) GSB_TRY(launch_stats_async(c, geom, sg, /*split=*/true, hdr, L, cap_k, cap_ks, st, &launches));
 
   float* dev_image = out_image;
   const size_t bytes = (size_t)W * H * 3 * sizeof(float);
   const bool host_out = !is_device_pointer(out_image);
   if (host_out) { GSB_TRY(c->image.ensure(bytes)); dev_image = c->image.as<float>(); }
-  if (!cover) GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, bytes, st));
-  const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
-  if (cu)
-    GSB_CUDA_TRY((cudaError_t)launch_composite_cu(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), c->bbox.as<float4>(),
-                                                  dev_image, geom, prm, st));
-  else
-    GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), sv, c->rec.as<float4>(), dev_image, geom, prm, nullptr, nullptr, st));
-  if (geom.tiles_x * geom.tiles_y > 0) ++launches;
-  tm.mark(GSB_STAGE_COMPOSITE);
+  auto queue_composite = [&](const uint32_t* abort) -> int {
+    if (!cover) GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, bytes, st));
+    if (cu)
+      GSB_CUDA_TRY((cudaError_t)launch_composite_cu(c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), c->rec.as<float4>(),
+                                                    c->bbox.as<float4>(), dev_image, geom, prm, abort, st));
+    else
+      GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), c->rec.as<float4>(),
+                                                 dev_image, geom, prm, nullptr, nullptr, abort, st));
+    if (tiles > 0) ++launches;
+    tm.mark(GSB_STAGE_COMPOSITE);
+    return GSB_OK;
+  };
+  GSB_TRY(run_split(c, m, nullptr, /*rows_sorted_by_visibility=*/false, geom, sg, hdr, L, st, tm, &launches, queue_composite));
+  c->info.m_in_view = m;
   if (host_out) GSB_CUDA_TRY(cudaMemcpyAsync(out_image, dev_image, bytes, cudaMemcpyDeviceToHost, st));
   c->info.kernel_launches = launches;
   c->frame_rows = m;
@@ -876,22 +1120,26 @@ int gsb_debug_projection(GsbContext* c, uint8_t* in_view, float* depth, float* p
   GSB_CUDA_TRY(cudaSetDevice(c->device));
   const int64_t n = c->frame_rows;
   if (n == 0) return GSB_OK;
+  GSB_CUDA_TRY(cudaDeviceSynchronize());  // the getters run on the legacy stream: order them after the frame's stream
   if (c->frame_projected) {
     // The frame variant of the projection writes no record for Gaussians without tiles and keys them like culled
     // ones; the getter reports every in-view row, so run the debug variant once more for the frame's camera
     // (identical values for the rows the frame did write; the control words it accumulates into are dead by now).
+    // It rewrites depth_key / count / rec: a frame saved for the backward pass is gone.
+    c->have_saved = false;
     FrameGeom geom{c->last_cam.width, c->last_cam.height, c->info.tiles_x, c->info.tiles_y};
+    const SuperGeom sg{0, 0, geom.tiles_x, geom.tiles_y};
     GSB_TRY(c->dbg_cov2d.ensure((size_t)n * 16));
     GSB_TRY(c->dbg_conic.ensure((size_t)n * 16));
     GSB_TRY(c->dbg_bbox.ensure((size_t)n * 16));
     DebugOut dbg{c->dbg_cov2d.as<float>(), c->dbg_conic.as<float>(), c->dbg_bbox.as<float>()};
-    const CtlLayout L = ctl_layout(geom, n, 0);
+    const CtlLayout L = ctl_layout(geom, sg, n, 0);
     GSB_TRY(c->control.ensure(L.total * 4));
     uint32_t* ctl = c->control.as<uint32_t>();
     GSB_CUDA_TRY((cudaError_t)launch_project(c->planes.as<float>(), n, c->n_pad, c->last_cam, c->last_prm, geom,
                                              c->depth_key.as<uint32_t>(), c->rec.as<float4>(), c->rect.as<ushort4>(),
                                              c->count.as<uint32_t>(), ctl, ctl + L.hist, 0,
-                                             reinterpret_cast<int32_t*>(ctl + L.grid), &dbg, 0));
+                                             reinterpret_cast<int32_t*>(ctl + L.grid), nullptr, sg, &dbg, 0));
   }
   // staging: u8[n] (padded to 4) | depth | pxy | radius | rect
   const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
@@ -916,6 +1164,7 @@ int gsb_debug_sorted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
   if (!c) return GSB_E_INVALID_ARG;
   if (!c->have_frame) return GSB_E_NO_FRAME;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
+  GSB_CUDA_TRY(cudaDeviceSynchronize());  // legacy-stream getter: order it after the frame's stream
   const size_t k = (size_t)c->info.k_instances;
   if (k == 0) return GSB_OK;
   const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
@@ -938,6 +1187,7 @@ int gsb_debug_emitted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
   if (!c) return GSB_E_INVALID_ARG;
   if (!c->have_frame || !c->emitted_valid) return GSB_E_NO_FRAME;  // multi-pass sorts recycle the emit buffer
   GSB_CUDA_TRY(cudaSetDevice(c->device));
+  GSB_CUDA_TRY(cudaDeviceSynchronize());
   const size_t k = (size_t)c->info.k_instances;
   if (k == 0) return GSB_OK;
   if (keys) GSB_CUDA_TRY(cudaMemcpy(keys, c->keys_a.p, k * 8, cudaMemcpyDefault));
@@ -949,6 +1199,7 @@ int gsb_debug_tile_ranges(GsbContext* c, uint32_t* ranges) {
   if (!c) return GSB_E_INVALID_ARG;
   if (!c->have_frame) return GSB_E_NO_FRAME;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
+  GSB_CUDA_TRY(cudaDeviceSynchronize());
   const size_t tiles = (size_t)c->info.tiles_x * c->info.tiles_y;
   if (tiles == 0) return GSB_OK;
   if (!ranges) return GSB_E_INVALID_ARG;

@@ -36,7 +36,12 @@ constexpr int kTile = 16;              // pixels per tile edge (the only size th
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
-constexpr int kCtlVisible = 4;  // word of the per-frame control header that counts the Gaussians WITH tiles (V)
+// words of the per-frame control header (zeroed once per frame)
+constexpr int kCtlM = 0;        // Gaussians in view
+constexpr int kCtlK = 2;        // tile instances, 64-bit (tile_stats_kernel, fine level)
+constexpr int kCtlVisible = 4;  // Gaussians WITH tiles (V)
+constexpr int kCtlAbort = 5;    // 1: a count exceeded the capacity the frame's tail was queued with -> those kernels return at once
+constexpr int kCtlKs = 6;       // super-tile instances, 64-bit (= K when the frame is binned in one level)
 
 // ---- scene planes ----
 enum Plane { PX = 0, PY, PZ, PSX, PSY, PSZ, PQW, PQX, PQY, PQZ, PR, PG, PB, POP, kNumPlanes };
@@ -44,6 +49,21 @@ enum Plane { PX = 0, PY, PZ, PSX, PSY, PSZ, PQW, PQX, PQY, PQZ, PR, PG, PB, POP,
 struct FrameGeom {
   int width, height;
   int tiles_x, tiles_y;
+};
+
+// SPLIT mode bins in two levels: super-tiles of 2^lw x 2^lh tiles (nx x ny of them), then tiles.  lw = lh = 0: one level.
+struct SuperGeom {
+  int lw, lh;
+  int nx, ny;
+};
+
+// what the (last) tile_stats launch of a frame reports besides its own total
+struct StatsPost {
+  int level;               // 0: fine grid (total -> ctl[kCtlK]), 1: super-tile grid (total -> ctl[kCtlKs])
+  int enabled;             // this launch decides ctl[kCtlAbort] and posts the mailbox
+  unsigned long long cap_k, cap_ks;  // capacities (in instances) the frame's tail was queued with
+  uint32_t* mailbox;       // mapped pinned host memory (device alias) or nullptr: {M, V, K lo, K hi, seq, abort, Ks lo, Ks hi}
+  uint32_t seq;
 };
 
 // extra per-Gaussian outputs written only by the debug/preprocess variant of the projection kernel
@@ -61,42 +81,43 @@ int launch_repack(const float* xyz, const float* scales, const float* quats, con
 // Without `dbg` (the frame variant) rows that touch no tile get depth_key 0xFFFFFFFF and no record / rect.
 // depth_hist: 4*256 zeroed words (digit histograms of the depth keys; weighted by tile count when
 // hist_weighted).  diff_grid: (tiles_x+1)*(tiles_y+1) zeroed ints (2-D difference grid of the tile rects).
+// super_grid (optional, with sg): (sg.nx+1)*(sg.ny+1) zeroed ints, the same for the super-tile rects.
+// Rows that touch no tile get rect = (1,0,1,0) (tx1 < tx0).
 int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
                    FrameGeom geom, uint32_t* depth_key, float4* rec, ushort4* rect, uint32_t* count,
                    uint32_t* m_counter, uint32_t* depth_hist, int hist_weighted, int32_t* diff_grid,
-                   const DebugOut* dbg, cudaStream_t st);
+                   int32_t* super_grid, SuperGeom sg, const DebugOut* dbg, cudaStream_t st);
 
-// 2-D prefix sum of the difference grid (in place) -> instances per tile -> per-tile [start,end) ranges
-// (empty tiles (0,0)), histograms of the tile-id digits (tile_hist: 4*256 zeroed words), total K.
-// host_mailbox (optional): mapped pinned host memory; receives {M, -, K lo, K hi, seq} (seq written last).
-int launch_tile_stats(int32_t* diff_grid, FrameGeom geom, uint32_t* tile_hist, uint2* ranges, uint32_t* k_total,
-                      const uint32_t* m_counter, uint32_t* host_mailbox, uint32_t seq, cudaStream_t st);
+// 2-D prefix sum of a difference grid (in place) -> instances per tile -> per-tile [start,end) ranges
+// (empty tiles (0,0)), histograms of the tile-id digits (tile_hist: 4*256 words, or nullptr), total -> ctl.
+int launch_tile_stats(int32_t* diff_grid, int tiles_x, int tiles_y, uint32_t* tile_hist, uint2* ranges, uint32_t* ctl,
+                      const StatsPost& post, cudaStream_t st);
 
 // exclusive scan of count[perm ? perm[i] : i] for i < n -> offsets[i] (u32, wraps if K >= 2^32: the host rejects
 // that from tile_stats' 64-bit total).  `status` needs scan_status_words(n) zeroed u32 words, 8-byte aligned.
 size_t scan_status_words(int64_t n);
 int launch_scan(const uint32_t* count, const uint32_t* perm, int64_t n, uint32_t* offsets, uint32_t* status,
                 cudaStream_t st);
-// `total`: device pointer to K (low word).  combined = false: keys = tile<<32 | depth bits, payload = Gaussian
-// index (FULL); combined = true: keys = tile<<32 | Gaussian index, payload untouched (SPLIT, keys-only passes);
-// combined with rank_bits > 0: 32-bit keys tile << rank_bits | emission position, written to `keys` as u32[K]
-// k: the host's copy of K (sizes the grid: one block per 8 192 output slots)
+// the same over the number of super-tiles each rect touches; rows at positions >= *v_limit (optional) are skipped
+int launch_scan_coarse(const ushort4* rect, SuperGeom sg, const uint32_t* perm, int64_t n, const uint32_t* v_limit,
+                       uint32_t* offsets, uint32_t* status, cudaStream_t st);
+// FULL mode: keys[o] = tile<<32 | depth bits, payload[o] = Gaussian index, in index order.  `total`: device pointer
+// to K (low word); k: the host's copy of K (sizes the grid: one block per 8 192 output slots)
 int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n, int64_t k,
-                const uint32_t* depth_key, const ushort4* rect, int tiles_x, bool combined, int rank_bits,
-                uint64_t* keys, uint32_t* payload, cudaStream_t st);
+                const uint32_t* depth_key, const ushort4* rect, int tiles_x, uint64_t* keys, uint32_t* payload,
+                cudaStream_t st);
+// SPLIT mode: one key per super-tile of the rect, in emission (depth) order: rank_bits > 0: u32 keys
+// super-tile << rank_bits | emission position; rank_bits == 0: u64 keys super-tile << 32 | Gaussian index.
+// The grid covers `capacity` keys; blocks past *total return, and nothing runs when *abort is set.
+int launch_emit_coarse(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
+                       const uint32_t* v_limit, const uint32_t* abort, int64_t capacity, const ushort4* rect,
+                       SuperGeom sg, int rank_bits, void* keys, cudaStream_t st);
+// per-tile lists from per-super-tile lists (stable compaction; the tile starts come from `ranges`)
+int launch_expand(const uint2* ranges_s, const uint32_t* cpay, const ushort4* rect, const uint2* ranges,
+                  uint32_t* payload, FrameGeom geom, SuperGeom sg, const uint32_t* abort, cudaStream_t st);
 // debug only: sorted keys tile<<32 | depth bits from ranges + sorted payload (SPLIT mode never stores them)
 int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
                         uint64_t* keys, cudaStream_t st);
-
-// ---- BINNED mode (binning.cu) ----
-int launch_invert_perm(const uint32_t* order, int64_t n, uint32_t* rank, cudaStream_t st);
-// cursor: one zeroed u32 per tile; payload[ranges[t].x + k] receives the Gaussian indices of tile t, unordered
-int launch_emit_binned(int64_t n, const ushort4* rect, const uint32_t* count, int tiles_x, const uint2* ranges,
-                       uint32_t* cursor, uint32_t* payload, cudaStream_t st);
-// sorts every tile segment of payload by rank[g]; rank_bits = ceil(log2(N)); scratch_{a,b}: K u32 each (only
-// touched by segments longer than the shared-memory capacity)
-int launch_tile_sort(const uint2* ranges, int tiles, const uint32_t* rank, const uint32_t* order, uint32_t* payload,
-                     int rank_bits, uint32_t* scratch_a, uint32_t* scratch_b, cudaStream_t st);
 
 // ---- onesweep radix sort ----
 struct SortPlan {
@@ -107,6 +128,9 @@ struct SortPlan {
   int low_bits;
   const uint32_t* gather_table;
   int wide_status;        // 1: 64-bit look-back words (2^30 keys and more)
+  const uint32_t* n_dev;  // optional: the key count lives on the device (u32); `n` is then the CAPACITY the grid and
+                          // the status words are sized for, tiles past *n_dev return at once
+  const uint32_t* abort;  // optional: nothing runs when *abort != 0
   int64_t n;
   int64_t tiles;          // onesweep tiles per pass
   size_t control_words;   // u32 words of control memory (tickets + look-back status), zeroed by the caller
@@ -128,8 +152,10 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
 
 // aux_t / aux_n (both or neither; save_for_backward): per pixel, transmittance after the last blended Gaussian
 // and the number of blended Gaussians (the prefix [0, n) of the tile's list)
+// abort (optional): device flag; the kernel returns at once when it is set (see kCtlAbort)
 int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
-                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, cudaStream_t st);
+                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, const uint32_t* abort,
+                     cudaStream_t st);
 
 // ---- backward pass (backward.cu) ----
 // grad2d: 12 zeroed floats per Gaussian row: d mean x,y | d a, d (b+c), d d (a b; c d = -0.5 inverse covariance) |
@@ -157,8 +183,11 @@ int launch_ingest_preprocessed(int64_t m, const float* means, const float* color
                                const float* min_x, const float* max_x, const float* min_y, const float* max_y,
                                const float* opacity, FrameGeom geom, const GsbParams& prm, uint32_t* depth_key,
                                float4* rec, float4* bbox, ushort4* rect, uint32_t* count, int32_t* diff_grid,
-                               cudaStream_t st);
+                               int32_t* super_grid, SuperGeom sg, cudaStream_t st);
 int launch_composite_cu(const uint2* ranges, const uint32_t* payload, const float4* rec, const float4* bbox,
-                        float* image, FrameGeom geom, const GsbParams& prm, cudaStream_t st);
+                        float* image, FrameGeom geom, const GsbParams& prm, const uint32_t* abort, cudaStream_t st);
+
+// number of SMs of the current device (cached per device)
+int sm_count();
 
 }  // namespace gsb

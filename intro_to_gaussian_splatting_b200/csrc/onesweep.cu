@@ -412,12 +412,17 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
 template <typename KeyT, int kItems, int kMode, typename W>
 __global__ void __launch_bounds__(kThreads, kItems == 8 ? 4 : GSB_SORT_MINBLOCKS16)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
-                uint32_t* __restrict__ vals_out, int64_t n, int shift, int bits,
+                uint32_t* __restrict__ vals_out, int64_t n, const uint32_t* __restrict__ n_dev,
+                const uint32_t* __restrict__ abort, int shift, int bits,
                 const uint32_t* __restrict__ hist /* [256] of this pass */, uint32_t* ticket,
                 W* status /* [num_tiles][256] */, uint32_t low_mask) {
   constexpr int kTileKeys = kThreads * kItems;
   __shared__ SortSmem<KeyT, kItems> sm;
   const int tid = threadIdx.x;
+  // device-side key count: the grid was sized for a capacity; CTAs whose ticket lies past the last tile leave
+  // (they come after every working CTA in ticket order, so no look-back ever waits for them)
+  if (abort && *abort) return;
+  if (n_dev) n = (int64_t)*n_dev;
   if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
   {
     uint4* z = reinterpret_cast<uint4*>(&sm.cnt[0][0]);
@@ -425,6 +430,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
   }
   __syncthreads();
   const uint32_t tile = sm.tile;
+  if ((int64_t)tile * kTileKeys >= n) return;
   const int valid = (int)min((int64_t)kTileKeys, n - (int64_t)tile * kTileKeys);
   const uint32_t mask = (1u << bits) - 1u;
   if (valid == kTileKeys)
@@ -460,6 +466,8 @@ SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
   p.keys_only = 0;
   p.low_bits = 0;
   p.gather_table = nullptr;
+  p.n_dev = nullptr;
+  p.abort = nullptr;
   p.items = g_sort_items;
   const int64_t tile_keys = (int64_t)kThreads * p.items;
   p.tiles = (n + tile_keys - 1) / tile_keys;
@@ -477,7 +485,8 @@ template <typename KeyT>
 int launch_key_histogram(const SortPlan& plan, const KeyT* keys, uint32_t* hist, cudaStream_t st) {
   if (plan.n == 0 || plan.passes == 0) return 0;
   int64_t chunks = (plan.n + kSortTile - 1) / kSortTile;
-  int hist_blocks = chunks < 148 * 4 ? (int)chunks : 148 * 4;
+  const int cap = sm_count() * 4;
+  int hist_blocks = chunks < cap ? (int)chunks : cap;
   histogram_kernel<KeyT><<<hist_blocks, kThreads, 0, st>>>(keys, plan.n, plan.begin_bit, plan.end_bit, plan.passes, hist);
   return (int)cudaGetLastError();
 }
@@ -486,14 +495,14 @@ template int launch_key_histogram<uint64_t>(const SortPlan&, const uint64_t*, ui
 
 template <typename KeyT, int kItems, typename W>
 static void launch_pass(int mode, unsigned tiles, cudaStream_t st, const KeyT* kin, const uint32_t* vin, KeyT* kout,
-                        uint32_t* vout, int64_t n, int shift, int bits, const uint32_t* hist, uint32_t* ticket,
-                        W* status, uint32_t low_mask) {
+                        uint32_t* vout, int64_t n, const uint32_t* n_dev, const uint32_t* abort, int shift, int bits,
+                        const uint32_t* hist, uint32_t* ticket, W* status, uint32_t low_mask) {
   if (mode == kPairs)
-    onesweep_kernel<KeyT, kItems, kPairs, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status, low_mask);
+    onesweep_kernel<KeyT, kItems, kPairs, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, n_dev, abort, shift, bits, hist, ticket, status, low_mask);
   else if (mode == kKeysOnly)
-    onesweep_kernel<KeyT, kItems, kKeysOnly, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status, low_mask);
+    onesweep_kernel<KeyT, kItems, kKeysOnly, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, n_dev, abort, shift, bits, hist, ticket, status, low_mask);
   else
-    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, bits, hist, ticket, status, low_mask);
+    onesweep_kernel<KeyT, kItems, kKeysOnlyLowOut, W><<<tiles, kThreads, 0, st>>>(kin, vin, kout, vout, n, n_dev, abort, shift, bits, hist, ticket, status, low_mask);
 }
 
 template <typename KeyT>
@@ -521,15 +530,15 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
     if (plan.wide_status) {
       uint64_t* stp = reinterpret_cast<uint64_t*>(status) + (size_t)p * per_pass;  // status starts 8-byte aligned
       if (plan.items == 16)
-        launch_pass<KeyT, 16, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
+        launch_pass<KeyT, 16, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, plan.n_dev, plan.abort, shift, bits, h, tickets + p, stp, low_mask);
       else
-        launch_pass<KeyT, 8, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
+        launch_pass<KeyT, 8, uint64_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, plan.n_dev, plan.abort, shift, bits, h, tickets + p, stp, low_mask);
     } else {
       uint32_t* stp = status + (size_t)p * per_pass;
       if (plan.items == 16)
-        launch_pass<KeyT, 16, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
+        launch_pass<KeyT, 16, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, plan.n_dev, plan.abort, shift, bits, h, tickets + p, stp, low_mask);
       else
-        launch_pass<KeyT, 8, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, shift, bits, h, tickets + p, stp, low_mask);
+        launch_pass<KeyT, 8, uint32_t>(mode, (unsigned)plan.tiles, st, kin, vin, kout, vout, plan.n, plan.n_dev, plan.abort, shift, bits, h, tickets + p, stp, low_mask);
     }
     if (launches) ++*launches;
     kin = kout; vin = vout;

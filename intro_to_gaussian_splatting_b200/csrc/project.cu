@@ -64,7 +64,10 @@ struct ProjectArgs {
   GsbCamera cam;
   float minimum_z, fov_clamp, det_min, lambda_floor, sigma_extent;
   int tile_size, tiles_x, tiles_y;
+  int super_lw, super_lh, super_nx, super_cells;  // super-tile grid of SPLIT mode (super_cells == 0: none)
 };
+
+constexpr int kMaxSuperCells = 576;  // (nx+1)*(ny+1) of a super-tile grid with nx*ny <= 256 never exceeds 514
 
 // [x y z 1] @ M[:, j] as torch's (N,4)@(4,4) evaluates it: one rounded product, then an FMA chain.
 __device__ __forceinline__ float rowvec_col(float x, float y, float z, const float* M, int j) {
@@ -117,17 +120,24 @@ __device__ __forceinline__ void tile_interval(float mn, float mx, int T, int nti
 //     mode, or weighted by the tile count for the 64-bit key sort of FULL mode;
 //   * a 2-D difference grid of the tile rects (+1,-1,-1,+1 at the rect corners, 4 REDs per Gaussian);
 //     its 2-D prefix sum (tile_stats_kernel) is the exact number of instances per tile, which yields
-//     the tile-digit histograms, the per-tile [start,end) ranges and K.
-// The grid is persistent (a multiple of the SM count) so that the histogram flush stays small.
+//     the tile-digit histograms, the per-tile [start,end) ranges and K;
+//   * the same difference grid one level up, for the super-tile rects of SPLIT mode's two-level binning: a few
+//     hundred cells that every Gaussian would hammer, so it is accumulated block-privately in shared memory and
+//     flushed once per block like the histograms.
+// The grid is persistent (a multiple of the SM count) so that the flushes stay small.
 template <bool kDebug>
 __global__ void __launch_bounds__(256, 4)
 project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const __grid_constant__ ProjectArgs a,
                uint32_t* __restrict__ depth_key, float4* __restrict__ rec, ushort4* __restrict__ rect,
                uint32_t* __restrict__ count, uint32_t* __restrict__ m_counter, uint32_t* __restrict__ depth_hist,
-               int hist_weighted, int32_t* __restrict__ diff_grid, DebugOut dbg) {
+               int hist_weighted, int32_t* __restrict__ diff_grid, int32_t* __restrict__ super_grid, DebugOut dbg) {
   __shared__ uint32_t s_hist[4][kRadix];
+  __shared__ int s_cg[kMaxSuperCells];
   __shared__ int s_cnt, s_vis;
   for (int t = threadIdx.x; t < 4 * kRadix; t += blockDim.x) (&s_hist[0][0])[t] = 0;
+  const bool cg_smem = a.super_cells <= kMaxSuperCells;  // (a two-pass super-tile grid is too big: global atomics then)
+  if (cg_smem)
+    for (int t = threadIdx.x; t < a.super_cells; t += blockDim.x) s_cg[t] = 0;
   if (threadIdx.x == 0) { s_cnt = 0; s_vis = 0; }
   __syncthreads();
   const int gw = a.tiles_x + 1;  // width of the difference grid
@@ -261,7 +271,6 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
         // the blend loop evaluates alpha = op2 * exp(power) as exp2(power*log2e + log2(op2)): one FFMA + MUFU.EX2
         rec[3 * i + 1] = make_float4(-0.5f * i10, -0.5f * i11, log2f(op2), cr);
         rec[3 * i + 2] = make_float4(cg, cb, rad, sig1);
-        rect[i] = make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1);
         dkey = __float_as_uint(vz);
       }
       if (kDebug) {
@@ -269,9 +278,10 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
         reinterpret_cast<float4*>(dbg.conic)[i] = make_float4(i00, i01, i10, i11);
         reinterpret_cast<float4*>(dbg.bbox)[i] = make_float4(mnx, mny, mxx, mxy);
       }
-    } else if (kDebug) {
-      rect[i] = make_ushort4(0, 0, 0, 0);
     }
+    // tx1 < tx0 marks "touches no tile" for everything downstream that reads rects without the count
+    rect[i] = cnt ? make_ushort4((unsigned short)tx0, (unsigned short)tx1, (unsigned short)ty0, (unsigned short)ty1)
+                  : make_ushort4(1, 0, 1, 0);
     count[i] = cnt;
     depth_key[i] = dkey;  // 0xFFFFFFFF when culled: sorts behind every real depth (z >= 0.2 > 0, finite)
     kept += keep ? 1 : 0;
@@ -290,6 +300,16 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
       atomicAdd(&diff_grid[ty0 * gw + tx1 + 1], -1);
       atomicAdd(&diff_grid[(ty1 + 1) * gw + tx0], -1);
       atomicAdd(&diff_grid[(ty1 + 1) * gw + tx1 + 1], 1);
+      if (a.super_cells) {
+        const int sx0 = tx0 >> a.super_lw, sx1 = (tx1 >> a.super_lw) + 1;
+        const int sy0 = ty0 >> a.super_lh, sy1 = (ty1 >> a.super_lh) + 1;
+        const int gs = a.super_nx + 1;
+        int* cg = cg_smem ? s_cg : super_grid;
+        atomicAdd(&cg[sy0 * gs + sx0], 1);
+        atomicAdd(&cg[sy0 * gs + sx1], -1);
+        atomicAdd(&cg[sy1 * gs + sx0], -1);
+        atomicAdd(&cg[sy1 * gs + sx1], 1);
+      }
     }
   }
   // M = number of in-view Gaussians, V = number that touch a tile: one atomic each per block
@@ -314,26 +334,34 @@ project_kernel(const float* __restrict__ planes, int64_t n, int64_t n_pad, const
     const uint32_t v = (&s_hist[0][0])[t];
     if (v) atomicAdd(&depth_hist[t], v);
   }
+  if (cg_smem)
+    for (int t = threadIdx.x; t < a.super_cells; t += blockDim.x) {
+      const int v = s_cg[t];
+      if (v) atomicAdd(&super_grid[t], v);
+    }
 }
 
 int launch_project(const float* planes, int64_t n, int64_t n_pad, const GsbCamera& cam, const GsbParams& prm,
                    FrameGeom geom, uint32_t* depth_key, float4* rec, ushort4* rect, uint32_t* count,
                    uint32_t* m_counter, uint32_t* depth_hist, int hist_weighted, int32_t* diff_grid,
-                   const DebugOut* dbg, cudaStream_t st) {
+                   int32_t* super_grid, SuperGeom sg, const DebugOut* dbg, cudaStream_t st) {
   if (n == 0) return 0;
   ProjectArgs a;
   a.cam = cam;
   a.minimum_z = prm.minimum_z; a.fov_clamp = prm.fov_clamp; a.det_min = prm.det_min;
   a.lambda_floor = prm.lambda_floor; a.sigma_extent = prm.sigma_extent;
   a.tile_size = prm.tile_size; a.tiles_x = geom.tiles_x; a.tiles_y = geom.tiles_y;
+  a.super_lw = sg.lw; a.super_lh = sg.lh; a.super_nx = sg.nx;
+  a.super_cells = super_grid ? (sg.nx + 1) * (sg.ny + 1) : 0;
   int64_t want = (n + 255) / 256;
-  unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);  // persistent: 8 CTAs per SM
+  const int64_t cap = (int64_t)sm_count() * 8;  // persistent: 8 CTAs per SM
+  unsigned blocks = (unsigned)(want < cap ? want : cap);
   if (dbg)
     project_kernel<true><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, depth_hist,
-                                                 hist_weighted, diff_grid, *dbg);
+                                                 hist_weighted, diff_grid, super_grid, *dbg);
   else
     project_kernel<false><<<blocks, 256, 0, st>>>(planes, n, n_pad, a, depth_key, rec, rect, count, m_counter, depth_hist,
-                                                  hist_weighted, diff_grid, DebugOut{});
+                                                  hist_weighted, diff_grid, super_grid, DebugOut{});
   return (int)cudaGetLastError();
 }
 

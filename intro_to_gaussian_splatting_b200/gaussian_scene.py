@@ -54,8 +54,7 @@ class GaussianScene(nn.Module):
             self.images[idx] = GaussianImage(camera=camera_dict[image.camera_id], image=image)
         self.gaussians = gaussians
         self.full_cover = bool(full_cover)  # False = the reference tile grid (last row/column never rendered)
-        self.sort_mode = {"auto": _lib.GSB_SORT_AUTO, "full": _lib.GSB_SORT_FULL, "split": _lib.GSB_SORT_SPLIT,
-                          "binned": _lib.GSB_SORT_BINNED}[sort_mode]
+        self.sort_mode = {"auto": _lib.GSB_SORT_AUTO, "full": _lib.GSB_SORT_FULL, "split": _lib.GSB_SORT_SPLIT}[sort_mode]
         self._rast: Optional[Rasterizer] = None
         self._uploaded_sig = None
 
@@ -78,15 +77,16 @@ class GaussianScene(nn.Module):
         # that neither their id() nor their storage address can be recycled by a replacement
         rast = self.rasterizer
         prev = self._uploaded_sig
-        same = prev is not None and all(a is b and a._version == v for a, (b, v) in zip(ts, prev))
+        # ... and the rasterizer's upload generation: somebody else (render_differentiable, fit) may have uploaded
+        # other tensors into this shared rasterizer since
+        same = (prev is not None and prev[0] == rast.upload_generation and
+                all(a is b and a._version == v for a, (b, v) in zip(ts, prev[1])))
         if not same:
             rast.upload(*ts)
-            self._uploaded_sig = tuple((t, t._version) for t in ts)
+            self._uploaded_sig = (rast.upload_generation, tuple((t, t._version) for t in ts))
         return rast
 
-    def _params(self, tile_size: int, semantics: str = "ref_cpu", **over):
-        if semantics not in ("ref_cpu", "ref_cu"):
-            raise ValueError(semantics)
+    def _params(self, tile_size: int, **over):
         return _lib.default_params(tile_size=int(tile_size), full_cover=int(self.full_cover), sort_mode=self.sort_mode, **over)
 
     # ---- the reference API ----------------------------------------------------------------------

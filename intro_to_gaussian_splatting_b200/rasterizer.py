@@ -39,6 +39,8 @@ class Rasterizer:
         check(self._lib.gsb_create(C.byref(h), self.device_index), "gsb_create")
         self._h = h
         self.n = 0
+        self.upload_generation = 0  # bumped by every upload(): owners of a shared rasterizer compare it (GaussianScene)
+        self.last_frame_id = 0      # GsbFrameInfo.frame_id of the last render() of this rasterizer
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -74,12 +76,15 @@ class Rasterizer:
             # block and synchronised inside gsb_upload -- no synchronisation is needed here
             check(self._lib.gsb_upload(self._h, n, *[_ptr(t) for t in ts], self._stream()), "gsb_upload")
         self.n = n
+        self.upload_generation += 1
 
     # ---- rendering ---------------------------------------------------------------------------
     def render(self, cam: GsbCamera, params: Optional[GsbParams] = None, out: Optional[torch.Tensor] = None,
                layout: str = "hwc") -> torch.Tensor:
         """One frame.  layout 'hwc' -> (H,W,3) like render.cu; 'whc' -> (W,H,3) like the CPU path;
-        'u8' -> (H,W,3) uint8.  `out` may be a CUDA tensor or a (pinned) CPU tensor."""
+        'u8' -> (H,W,3) uint8.  `out` may be a CUDA tensor on this rasterizer's device or a (pinned) CPU tensor.
+        A CPU `out` is complete when the call returns, EXCEPT with params.async_host_copy = 1, where the copy runs on
+        the context's copy stream: call join_host_copies() and synchronise the current stream before reading it."""
         params = params or _lib.default_params()
         H, W = cam.height, cam.width
         shape, dtype = {"hwc": ((H, W, 3), torch.float32), "whc": ((W, H, 3), torch.float32),
@@ -88,24 +93,34 @@ class Rasterizer:
             out = torch.empty(shape, dtype=dtype, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
             raise RuntimeError(f"render: out must be contiguous {dtype} of shape {shape}")
+        if out.is_cuda and out.device != self.device:
+            raise RuntimeError("render: `out` lives on a different GPU than the rasterizer")
         fn = {"hwc": self._lib.gsb_render, "whc": self._lib.gsb_render_wh, "u8": self._lib.gsb_render_u8}[layout]
         with torch.cuda.device(self.device):
             check(fn(self._h, C.byref(cam), C.byref(params), _ptr(out), self._stream()), "gsb_render")
+            if not out.is_cuda and not params.async_host_copy:
+                torch.cuda.current_stream(self.device).synchronize()  # the caller may read a CPU `out` right away
+        self.last_frame_id = int(self.frame_info().frame_id)
         return out
 
-    def render_backward(self, cam: GsbCamera, params: GsbParams, grad_image: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def render_backward(self, cam: GsbCamera, params: GsbParams, grad_image: torch.Tensor,
+                        frame_id: int = 0) -> Dict[str, torch.Tensor]:
         """Gradients of the last `render(cam, params)` of this rasterizer (params.save_for_backward must have been
         1) for dL/d image = grad_image (H,W,3): dict with points (N,3), scales (N,3), quaternions (N,4),
-        colors (N,3), opacity (N,1) -- the reference's attribute names (splat/gaussians.py:19-33)."""
+        colors (N,3), opacity (N,1) -- the reference's attribute names (splat/gaussians.py:19-33).
+        frame_id: `last_frame_id` as it was right after the render being differentiated (0: do not check); the
+        call fails with GSB_E_NO_SAVED when anything else ran on the rasterizer in between."""
         H, W = cam.height, cam.width
         g = _f32c(grad_image)
         if tuple(g.shape) != (H, W, 3):
             raise RuntimeError(f"render_backward: grad_image must have shape {(H, W, 3)}, got {tuple(g.shape)}")
+        if g.is_cuda and g.device != self.device:
+            raise RuntimeError("render_backward: grad_image lives on a different GPU than the rasterizer")
         n, dev = self.n, self.device
         out = {k: torch.empty((n, w), dtype=torch.float32, device=dev)
                for k, w in (("points", 3), ("scales", 3), ("quaternions", 4), ("colors", 3), ("opacity", 1))}
         with torch.cuda.device(self.device):
-            check(self._lib.gsb_render_backward(self._h, C.byref(cam), C.byref(params), _ptr(g),
+            check(self._lib.gsb_render_backward(self._h, C.byref(cam), C.byref(params), int(frame_id), _ptr(g),
                                                 *[_ptr(out[k]) for k in ("points", "scales", "quaternions", "colors",
                                                                          "opacity")], self._stream()),
                   "gsb_render_backward")

@@ -52,11 +52,12 @@ class Params(C.Structure):
         ("collect_stage_times", C.c_int32),
         ("async_host_copy", C.c_int32),
         ("save_for_backward", C.c_int32),
+        ("cull_alpha", C.c_float),
     ]
 
 
 def default_params(**over) -> Params:
-    p = Params(16, 0.2, 1.3, 1e-3, 0.1, 3.0, 1e-6, 0.99, 0, 0, 0, 0, 0)
+    p = Params(16, 0.2, 1.3, 1e-3, 0.1, 3.0, 1e-6, 0.99, 0, 0, 0, 0, 0, 0, 2.0 ** -30)
     for k, v in over.items():
         setattr(p, k, v)
     return p

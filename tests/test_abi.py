@@ -25,13 +25,13 @@ def test_header_and_library_agree():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in gsb.h but not exported"
-    assert lib.gsb_version() == 1
+    assert lib.gsb_version() == _lib.GSB_API_VERSION == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.GsbCamera) == 16 * 4 * 2 + 4 * 4 + 2 * 4
-    assert C.sizeof(_lib.GsbParams) == 14 * 4
-    assert C.sizeof(_lib.GsbFrameInfo) == 3 * 8 + 6 * 4
+    assert C.sizeof(_lib.GsbParams) == 15 * 4
+    assert C.sizeof(_lib.GsbFrameInfo) == 3 * 8 + 6 * 4 + 2 * 8 + 2 * 4
 
 
 def test_struct_layouts_match_a_c_compiler(tmp_path):

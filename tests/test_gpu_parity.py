@@ -57,7 +57,7 @@ def _check_frame_against_oracle(rast, fr, prm, check_pixels_img=None):
     assert np.array_equal(rng, fr.ranges), "tile ranges differ"
 
 
-@pytest.mark.parametrize("sort_mode", [_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT, _lib.GSB_SORT_BINNED])
+@pytest.mark.parametrize("sort_mode", [_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT])
 @pytest.mark.parametrize("name,base,nv,view", [("tiny", "tiny", 1, 1), ("small", "small", 1, 1),
                                                ("orbit", "small", 4, 3), ("cfg1", "cfg1", 1, 1)])
 def test_small_scenes_vs_reference_goldens(rast, name, base, nv, view, sort_mode):
@@ -111,9 +111,8 @@ def test_preprocess_hashes_full_size(rast, name):
 
 
 @pytest.mark.parametrize("name,full_cover,sort_mode", [("cfg2", 0, _lib.GSB_SORT_SPLIT), ("cfg2", 1, _lib.GSB_SORT_FULL),
-                                                       ("cfg2", 0, _lib.GSB_SORT_BINNED), ("cfg3", 0, _lib.GSB_SORT_FULL),
-                                                       ("cfg3", 1, _lib.GSB_SORT_SPLIT), ("cfg3", 1, _lib.GSB_SORT_BINNED),
-                                                       ("cfg3", 0, _lib.GSB_SORT_BINNED)])
+                                                       ("cfg3", 0, _lib.GSB_SORT_FULL),
+                                                       ("cfg3", 1, _lib.GSB_SORT_SPLIT), ("cfg3", 0, _lib.GSB_SORT_SPLIT)])
 def test_baseline_configs_vs_oracle(rast, name, full_cover, sort_mode):
     """BASELINE configs 2 and 3 at full size: keys/ranges bit-exact, pixels <= 1e-4 vs the oracle."""
     sc, images, _ = scene_and_images(name)
@@ -165,7 +164,7 @@ def test_edge_cases(rast):
         arrs = (xyz, s2.scales, s2.quats, (s2.rgb255 / 256).float(), s2.opacity_logit)
         rast.upload(*[a.cuda() for a in arrs])
         for fc in (0, 1):
-            for sm in (_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT, _lib.GSB_SORT_BINNED):
+            for sm in (_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT):
                 p = _lib.default_params(full_cover=fc, sort_mode=sm)
                 img = rast.render(im2[1].pack(), p)
                 torch.cuda.synchronize()

@@ -85,7 +85,7 @@ def test_degenerate_inputs(rast):
     xyz[90:100] = xyz[90]                    # ten coincident Gaussians: equal depth, tie order by index
     col[100:110] = 0.0
     arrs = [xyz, scales, quats, col, op]
-    for sm in (_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT, _lib.GSB_SORT_BINNED):
+    for sm in (_lib.GSB_SORT_FULL, _lib.GSB_SORT_SPLIT):
         for fc in (0, 1):
             _compare(rast, cam, _lib.default_params(full_cover=fc, sort_mode=sm), arrs)
     # PreprocessedScene of the same set, against the oracle, bit for bit (NaN patterns included)
