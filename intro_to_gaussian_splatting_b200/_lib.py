@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libgsb_b200.so")
+# GSB_LIB_PATH: load another build of the same library (A/B runs of kernel variants); never a different backend
+LIB_PATH = os.environ.get("GSB_LIB_PATH") or os.path.join(_PKG_DIR, "libgsb_b200.so")
 
 GSB_SEM_REF_CPU = 0
 GSB_SEM_REF_CU = 1

@@ -8,12 +8,12 @@
 // tile_stats_kernel derives them from the 2-D difference grid of tile rects written by the projection kernel.
 //
 //
-// SPLIT mode does the expansion in two levels: the Gaussians, already in depth order, are
-// first expanded into SUPER-TILE instances (a super-tile is 2^lw x 2^lh tiles, chosen so that the frame has at most
-// 256 of them: 8x4 tiles at 1080p), those few keys take ONE stable radix pass over the super-tile id, and
-// expand_kernel then derives every tile's list from its super-tile's list with a stable warp-wide compaction --
-// the per-tile start offsets are known up front from tile_stats_kernel, so no key is ever written per tile
-// instance and nothing K-sized is sorted.
+// SPLIT mode bins in two levels: the Gaussians, already in depth order, are expanded into
+// SUPER-TILE instances (a super-tile is 8 x 4 tiles: 255 of them at 1080p), those few keys take one stable radix
+// pass per 8 bits of super-tile id (one at 1080p), and the last pass leaves, per instance, the Gaussian index and a
+// 32-bit mask of the tiles of the super-tile that the rect covers.  A tile's list is its super-tile's list filtered
+// by one bit; the compositing kernel does that on the fly, so no key is ever written per tile instance, nothing
+// K-sized is sorted, and nothing K-sized is even stored.
 //
 // Roofline: HBM.  scan: 12 B read + 4 B written per Gaussian.  emit: 4-12 B written per key (+ 24 B per Gaussian
 // read).  tile stats: 4 B per grid cell read, 8 B per tile written.  expand: 4 B written per tile instance.
@@ -171,10 +171,11 @@ int launch_scan_coarse(const ushort4* rect, SuperGeom sg, const uint32_t* perm, 
 }
 
 enum EmitKind { kEmitFull = 0, kEmitSplit64 = 1, kEmitSplit32 = 2 };
-#ifndef GSB_EMIT_CHUNK
-#define GSB_EMIT_CHUNK 8192
-#endif
-constexpr int kEmitChunk = GSB_EMIT_CHUNK;   // output slots per block
+// output slots per block: 8 192 for the tile-instance keys of FULL mode (~350 Gaussians per block: one staging
+// window), 2 048 for the super-tile keys of SPLIT mode (a Gaussian emits 3-4 of those, so a block of 8 192 slots
+// would walk 4-16 windows of dependent order -> rect gathers back to back: measured 46 us for 1.35 M keys)
+constexpr int kEmitChunkFull = 8192;
+constexpr int kEmitChunkSuper = 2048;
 constexpr int kEmitWindow = 512;   // Gaussians staged per window
 constexpr uint32_t kEmitRun = 16;  // consecutive output slots per thread and search
 
@@ -182,7 +183,7 @@ constexpr uint32_t kEmitRun = 16;  // consecutive output slots per thread and se
 // lw = lh = 0 that is one key per tile.  The grid is sized from the CAPACITY of the key buffer, not from the key
 // count (which only the device knows when the kernel is queued): blocks past *total leave at once, and nothing
 // runs when *abort is set (the count exceeded the capacity; the host re-queues the frame's tail after growing).
-template <int kKind>
+template <int kKind, int kEmitChunk>
 __global__ void __launch_bounds__(kEmitThreads)
 emit_kernel(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ total,
             int64_t n, const uint32_t* __restrict__ v_limit, const uint32_t* __restrict__ abort,
@@ -325,8 +326,8 @@ int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* t
                 const uint32_t* depth_key, const ushort4* rect, int tiles_x, uint64_t* keys, uint32_t* payload,
                 cudaStream_t st) {
   if (n == 0 || k <= 0) return 0;
-  unsigned blocks = (unsigned)((k + kEmitChunk - 1) / kEmitChunk);
-  emit_kernel<kEmitFull><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, nullptr, nullptr, depth_key, rect,
+  unsigned blocks = (unsigned)((k + kEmitChunkFull - 1) / kEmitChunkFull);
+  emit_kernel<kEmitFull, kEmitChunkFull><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, nullptr, nullptr, depth_key, rect,
                                                           tiles_x, 0, 0, 0, keys, payload);
   return (int)cudaGetLastError();
 }
@@ -335,13 +336,13 @@ int launch_emit_coarse(const uint32_t* offsets, const uint32_t* perm, const uint
                        const uint32_t* v_limit, const uint32_t* abort, int64_t capacity, const ushort4* rect,
                        SuperGeom sg, int rank_bits, void* keys, cudaStream_t st) {
   if (n == 0 || capacity <= 0) return 0;
-  unsigned blocks = (unsigned)((capacity + kEmitChunk - 1) / kEmitChunk);
+  unsigned blocks = (unsigned)((capacity + kEmitChunkSuper - 1) / kEmitChunkSuper);
   if (rank_bits > 0)
-    emit_kernel<kEmitSplit32><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, v_limit, abort, nullptr, rect,
+    emit_kernel<kEmitSplit32, kEmitChunkSuper><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, v_limit, abort, nullptr, rect,
                                                                sg.nx, sg.lw, sg.lh, rank_bits,
                                                                reinterpret_cast<uint64_t*>(keys), nullptr);
   else
-    emit_kernel<kEmitSplit64><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, v_limit, abort, nullptr, rect,
+    emit_kernel<kEmitSplit64, kEmitChunkSuper><<<blocks, kEmitThreads, 0, st>>>(offsets, perm, total, n, v_limit, abort, nullptr, rect,
                                                                sg.nx, sg.lw, sg.lh, 0,
                                                                reinterpret_cast<uint64_t*>(keys), nullptr);
   return (int)cudaGetLastError();
@@ -367,81 +368,68 @@ int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload,
 }
 
 // ------------------------------------------------------------------------------------------------
-// expand: per-tile lists from per-super-tile lists (SPLIT mode, second level).
+// expand: per-tile lists from per-super-tile lists (SPLIT mode; ON DEMAND only).
 //
-// After the one radix pass over the super-tile ids, cpay[ranges_s[s].x .. ranges_s[s].y) holds the Gaussians whose
-// rect touches super-tile s, in depth order.  Tile t of s needs exactly those of them whose rect covers t, in the
-// same order, at payload[ranges[t].x ..] -- a stable stream compaction, and the destination of every tile is known
-// before the first key exists (tile_stats_kernel).  One warp per tile: 32 list entries per step, one ballot, the
-// hits leave as one run of consecutive 4-byte stores.  The 16 warps of a CTA serve 16 tiles of the same super-tile
-// and share its list through shared memory (512 entries per window: index + rect gathered once per CTA,
-// prefetched one window ahead in registers).  No atomics, no look-back, no key: deterministic by construction.
-//
-// Work: tiles * (super-tile list length / 32) warp-steps of ~14 instructions -- a fraction of what a radix pass over
-// the K tile instances executes, and the only K-sized traffic is the 4 B per instance this kernel writes.
+// After the radix pass(es) over the super-tile ids, clist[ranges_s[s].x .. ranges_s[s].y) holds one entry
+// {Gaussian index, tile mask} per Gaussian whose rect touches super-tile s, in depth order; bit ly << lw | lx of the
+// mask says whether the rect covers tile (lx, ly) of the super-tile (at most 32 tiles: one word).  The list of tile
+// t is exactly the entries of its super-tile whose bit t is set, in the same order.  The compositing kernel reads
+// the super-tile lists directly and filters on the fly (composite.cu), so the frame path never materialises the
+// per-tile lists; this kernel does it for whoever wants them as arrays: the parity surface (gsb_debug_sorted_keys)
+// and nothing else.  One warp per tile: 32 entries per step, one ballot, the hits leave as one run of consecutive
+// 4-byte stores at payload[ranges[t].x ..] -- the starts are known from tile_stats_kernel.  No atomics, no keys.
 // ------------------------------------------------------------------------------------------------
 constexpr int kExpWarps = 16;
 constexpr int kExpThreads = kExpWarps * 32;
 
 __global__ void __launch_bounds__(kExpThreads)
-expand_kernel(const uint2* __restrict__ ranges_s, const uint32_t* __restrict__ cpay, const ushort4* __restrict__ rect,
-              const uint2* __restrict__ ranges, uint32_t* __restrict__ payload, int tiles_x, int tiles_y, int snx,
-              int lw, int lh, const uint32_t* __restrict__ abort) {
-  __shared__ uint32_t s_g[2][kExpThreads];
-  __shared__ uint2 s_r[2][kExpThreads];
+expand_kernel(const uint2* __restrict__ ranges_s, const uint2* __restrict__ clist, const uint2* __restrict__ ranges,
+              uint32_t* __restrict__ payload, int tiles_x, int tiles_y, int snx, int lw, int lh,
+              const uint32_t* __restrict__ abort) {
+  __shared__ uint2 s_e[2][kExpThreads];
   if (abort && *abort) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per_super = 1 << (lw + lh - 4);  // CTAs per super-tile (a super-tile has at least 16 tiles)
+  const int per_super = ((1 << (lw + lh)) + kExpWarps - 1) / kExpWarps;  // CTAs per super-tile
   const int s = blockIdx.x / per_super, sub = blockIdx.x - s * per_super;
   const int lt = sub * kExpWarps + warp;     // tile inside the super-tile, row-major
   const uint32_t tx = (uint32_t)(((s % snx) << lw) + (lt & ((1 << lw) - 1)));
   const uint32_t ty = (uint32_t)(((s / snx) << lh) + (lt >> lw));
-  const bool valid = tx < (uint32_t)tiles_x && ty < (uint32_t)tiles_y;
+  const bool valid = lt < (1 << (lw + lh)) && tx < (uint32_t)tiles_x && ty < (uint32_t)tiles_y;
   const uint2 rs = ranges_s[s];
   const uint32_t len = rs.y - rs.x;
-  const uint32_t* list = cpay + rs.x;
+  const uint2* list = clist + rs.x;
   uint32_t out = valid ? ranges[ty * (uint32_t)tiles_x + tx].x : 0u;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  uint32_t g_next = 0;
-  uint2 r_next = make_uint2(1u, 1u);
-  auto fetch = [&](uint32_t w0) {
-    if (w0 + tid < len) {
-      g_next = list[w0 + tid];
-      r_next = *reinterpret_cast<const uint2*>(rect + g_next);  // (tx0 | tx1 << 16, ty0 | ty1 << 16)
-    }
-  };
-  fetch(0);
+  uint2 e_next = make_uint2(0u, 0u);
+  if ((uint32_t)tid < len) e_next = list[tid];
   for (uint32_t w0 = 0, it = 0; w0 < len; w0 += kExpThreads, ++it) {
     const int buf = (int)(it & 1u);
-    s_g[buf][tid] = g_next;
-    s_r[buf][tid] = r_next;
+    s_e[buf][tid] = e_next;
     __syncthreads();  // also orders the reads of this buffer two windows ago before the writes above
-    fetch(w0 + kExpThreads);
+    if (w0 + kExpThreads + tid < len) e_next = list[w0 + kExpThreads + tid];
     const uint32_t cnt = len - w0 < (uint32_t)kExpThreads ? len - w0 : (uint32_t)kExpThreads;
     if (valid) {
       for (uint32_t c = 0; c < cnt; c += 32) {
         const uint32_t e = c + lane;
-        bool hit = false;
-        if (e < cnt) {
-          const uint2 r = s_r[buf][e];
-          hit = (r.x & 0xFFFFu) <= tx && tx <= (r.x >> 16) && (r.y & 0xFFFFu) <= ty && ty <= (r.y >> 16);
-        }
+        uint2 v = make_uint2(0u, 0u);
+        if (e < cnt) v = s_e[buf][e];
+        const bool hit = e < cnt && ((v.y >> lt) & 1u);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) payload[out + (uint32_t)__popc(m & lt_mask)] = s_g[buf][e];
+        if (hit) payload[out + (uint32_t)__popc(m & lt_mask)] = v.x;
         out += (uint32_t)__popc(m);
       }
     }
   }
 }
 
-int launch_expand(const uint2* ranges_s, const uint32_t* cpay, const ushort4* rect, const uint2* ranges,
-                  uint32_t* payload, FrameGeom geom, SuperGeom sg, const uint32_t* abort, cudaStream_t st) {
+int launch_expand(const uint2* ranges_s, const uint2* clist, const uint2* ranges, uint32_t* payload, FrameGeom geom,
+                  SuperGeom sg, const uint32_t* abort, cudaStream_t st) {
   const int supers = sg.nx * sg.ny;
-  if (supers <= 0 || sg.lw + sg.lh < 4) return 0;
-  const unsigned blocks = (unsigned)supers << (sg.lw + sg.lh - 4);
-  expand_kernel<<<blocks, kExpThreads, 0, st>>>(ranges_s, cpay, rect, ranges, payload, geom.tiles_x, geom.tiles_y, sg.nx,
-                                                sg.lw, sg.lh, abort);
+  if (supers <= 0) return 0;
+  const int per_super = ((1 << (sg.lw + sg.lh)) + kExpWarps - 1) / kExpWarps;
+  expand_kernel<<<(unsigned)(supers * per_super), kExpThreads, 0, st>>>(ranges_s, clist, ranges, payload, geom.tiles_x,
+                                                                       geom.tiles_y, sg.nx, sg.lw, sg.lh, abort);
   return (int)cudaGetLastError();
 }
 

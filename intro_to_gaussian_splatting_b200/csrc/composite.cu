@@ -141,9 +141,17 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 // exactly like `return pixel_color` at splat/gaussian_scene.py:166-167.  Every 4 Gaussians the warp
 // votes and leaves when no pixel is live.
 //
-// Staging: records are copied global->shared with cp.async (LDGSTS, 3 x 16 B per record, no register
-// staging) into a double buffer, one batch ahead of the blend loop; the payload index of the batch
-// after that is prefetched into a register so the cp.async addresses are ready when the buffer frees.
+// Where the tile's list comes from (kMasked).  SPLIT mode never stores per-tile lists: the tile reads the list of
+// its SUPER-TILE (8 x 4 tiles; entries {Gaussian index, 32-bit tile mask} in depth order, written by the last radix
+// pass) and keeps the entries whose mask has the tile's bit -- 128 entries per round, two ballots per warp, the
+// survivors' indices go into a small ring in shared memory.  Early termination therefore also ends the binning
+// work: a tile that saturates after 350 Gaussians never looks at the rest of its super-tile's list, where a
+// separate expansion pass would have written (and this kernel read back) all of it.  FULL mode and one-level SPLIT
+// feed the same ring from a materialised per-tile payload array (every entry a hit).
+//
+// Staging: the ring's next 128 indices are turned into records with cp.async (LDGSTS, 3 x 16 B per record, no
+// register staging) into a double buffer, one batch ahead of the blend loop; the entries of the filter round after
+// that are prefetched into registers across the blend loop.
 //
 // Per-warp culling.  The reference has no per-pixel bounding-box test: every pixel of a
 // tile evaluates every Gaussian of the tile's list, and for a large share of those steps alpha is exactly 0 in
@@ -154,17 +162,19 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 // proportional to the magnitude of the cancelling terms covers the difference between the real-valued quadratic
 // and the kernel's (the reference's) fp32 evaluation order, so ill-conditioned conics are simply never culled.
 // One ballot per (record slot, warp footprint) turns the verdicts into a 128-bit survivor mask per warp and
-// batch, and the blend loop walks the set bits only.  With cull_alpha = 0 only steps whose alpha is exactly zero
-// are skipped (bit-identical frames); with cull_alpha = t > 0 a skipped step would have changed a pixel by less
-// than t (T and live are untouched for alpha < 2^-25), so the frame differs by < t * (list length).
+// batch; each warp compacts its mask into a byte list of record slots (padded to a multiple of four with the slot
+// of a null record) and walks that list four at a time -- straight-line code with all twelve LDS of a group
+// issued up front.  (Walking the mask bits directly costs a data-dependent branch per record and serialises the
+// loads: measured 491 us against 409 us for the frame's compositing with nothing culled.)  With cull_alpha = 0
+// only steps whose alpha is exactly zero are skipped (bit-identical frames); with cull_alpha = t > 0 a skipped step
+// would have changed a pixel by less than t (T and live are untouched for alpha < 2^-25), so the frame differs by
+// < t * (list length).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastThreads = 64;
 constexpr int kFastBatch = 128;                        // records per stage
 constexpr int kFastPerThread = kFastBatch / kFastThreads;  // records each thread stages
-#ifndef GSB_FAST_UNROLL
-#define GSB_FAST_UNROLL 4
-#endif
-constexpr int kFastUnroll = GSB_FAST_UNROLL;                 // Gaussians between two warp votes
+constexpr int kFastUnroll = 4;                         // Gaussians between two warp votes = slots per list word
+constexpr int kRing = 256;                             // survivor ring: < 128 pending + <= 128 from one round
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -204,33 +214,79 @@ __device__ __forceinline__ bool may_contribute(float A, float B, float C, float 
 
 // kAux (save_for_backward): also records, per pixel, the length of the list prefix that reached the pixel (index of
 // the last blended Gaussian + 1) and the transmittance after it -- what the back-to-front gradient pass starts
-// from (backward.cu).
-template <bool kAux>
-__global__ void __launch_bounds__(kFastThreads)
-composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
-                      const float4* __restrict__ rec, float* __restrict__ image, float* __restrict__ aux_t,
-                      uint32_t* __restrict__ aux_n, const uint32_t* __restrict__ abort,
+// from (backward.cu) -- and, when the list is filtered on the fly (kMasked), writes the tile's list to
+// src.payload_out as it is consumed: the gradient pass walks exactly that prefix.
+// One (pixel, Gaussian) step in the reference's own rounding order (compute_gaussian_weight, splat/utils.py:363-364):
+// ((-0.5 d) @ inv) is an FMA chain in k order, (.) @ d^T two rounded products and a rounded sum.  Expects q0, q1, q2,
+// dx, ta_, tb_, minw, nbase, i in scope.
+#define GSB_PIXEL_STEP(FY, T, LIVE, R, G, B, NC, TF)                                       \
+          {                                                                                \
+            const float dy = q0.y - FY;                                                    \
+            const float u0 = __fmaf_rn(dy, q1.x, ta_);                                     \
+            const float u1 = __fmaf_rn(dy, q1.y, tb_);                                     \
+            const float pw = __fadd_rn(__fmul_rn(u0, dx), __fmul_rn(u1, dy));              \
+            const float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z)); /* q1.z = log2(op) */ \
+            const float ta = T * al;                                                       \
+            T = T - ta;                                                                    \
+            LIVE = LIVE && (T >= minw);                                                    \
+            if (LIVE) { R = fmaf(ta, q1.w, R); G = fmaf(ta, q2.x, G); B = fmaf(ta, q2.y, B); } \
+            if (kAux) { if (LIVE && i < (uint32_t)kFastBatch) { NC = nbase + i; TF = T; } }  \
+          }
+
+#ifndef GSB_FAST_MINBLOCKS
+#define GSB_FAST_MINBLOCKS 9
+#endif
+template <bool kAux, bool kMasked>
+__global__ void __launch_bounds__(kFastThreads, GSB_FAST_MINBLOCKS)
+composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __restrict__ rec, float* __restrict__ image,
+                      float* __restrict__ aux_t, uint32_t* __restrict__ aux_n, const uint32_t* __restrict__ abort,
                       const __grid_constant__ CompositeArgs a) {
-  __shared__ __align__(16) float4 sm[2][kFastBatch * 3];
+  __shared__ __align__(16) float4 sm[2][(kFastBatch + 1) * 3];      // record double buffer; slot 128 = null record
   __shared__ __align__(16) uint32_t s_mask[2][2][kFastBatch / 32];  // [buffer][warp footprint][survivor bits]
+  __shared__ uint32_t s_ring[kRing];                                // Gaussian indices of the tile's list, in order
+  __shared__ __align__(8) uint16_t s_list[2][kFastBatch + 8];       // per warp: shared-memory addresses (16 bits) of the
+                                                                    // records that survive culling
+  __shared__ uint32_t s_cnt[2][4];                                  // filter round: hits per (warp, entry half)
+  __shared__ uint32_t s_dead[2];                                    // warp w has no live pixel left
   if (abort && *abort) return;  // the lists do not exist: the host re-queues the frame's tail (gsb_api.cu)
 
   const int tile = blockIdx.x;
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int px = tx * kTile + (lane & 15);
   const int py0 = ty * kTile + warp * 8 + (lane >> 4) * 4;
   const float fx = (float)px;
   const float fy0 = (float)py0, fy1 = (float)(py0 + 1), fy2 = (float)(py0 + 2), fy3 = (float)(py0 + 3);
   const float minw = a.min_weight;
   const float cull = a.cull_log2;
+  const bool cull_on = cull > -INFINITY;
   // pixel rectangles of the two warps (columns shared)
   const float rx0 = (float)(tx * kTile), rx1 = rx0 + (float)(kTile - 1);
   const float ry0 = (float)(ty * kTile), ry1 = ry0 + 7.f, ry2 = ry0 + 8.f, ry3 = ry0 + 15.f;
 
-  const uint2 rg = ranges[tile];
-  const uint32_t len = rg.y - rg.x;
-  const uint32_t* pl = payload + rg.x;
+  // the list this tile filters: its super-tile's entries (kMasked) or its own payload slice
+  uint32_t len, my_bit = 0;
+  const uint2* cl = nullptr;
+  const uint32_t* pl = nullptr;
+  uint32_t* out_list = nullptr;
+  if (kMasked) {
+    const int s = (ty >> src.lh) * src.snx + (tx >> src.lw);
+    const uint2 rs = src.ranges_s[s];
+    len = rs.y - rs.x;
+    cl = src.clist + rs.x;
+    my_bit = (uint32_t)(((ty & ((1 << src.lh) - 1)) << src.lw) | (tx & ((1 << src.lw) - 1)));
+    if (kAux) out_list = src.payload_out + src.ranges[tile].x;
+  } else {
+    const uint2 rg = src.ranges[tile];
+    len = rg.y - rg.x;
+    pl = src.payload + rg.x;
+  }
+  if (tid < 2) {  // null record: log2(opacity) = -inf => alpha = 0 => an exact no-op for T, live and the colours
+    float4* d = &sm[tid][kFastBatch * 3];
+    d[0] = make_float4(0.f, 0.f, 0.f, 0.f); d[1] = make_float4(0.f, 0.f, -INFINITY, 0.f); d[2] = d[0];
+    s_dead[tid] = 0u;
+  }
 
   bool l0 = px < a.width && py0 < a.height, l1 = px < a.width && py0 + 1 < a.height;
   bool l2 = px < a.width && py0 + 2 < a.height, l3 = px < a.width && py0 + 3 < a.height;
@@ -240,100 +296,133 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;          // kAux only
   float tf0 = 1.f, tf1 = 1.f, tf2 = 1.f, tf3 = 1.f;  // kAux only
 
-  // stage batch `b` (records b*128 .. b*128+127) into buffer `buf`; idx[] holds this thread's payload indices
-  uint32_t idx[kFastPerThread];
-  auto load_idx = [&](uint32_t b) {
+  // ---- list filter: entries pos .. pos+127 per round, hits appended to the ring ----
+  uint32_t pos = 0, head = 0, tail = 0;  // entries examined; ring indices consumed / produced (uniform over the CTA)
+  uint32_t e_g[kFastPerThread], e_hit[kFastPerThread];
+  auto prefetch = [&]() {  // this thread's entries of the next round: pos + tid and pos + 64 + tid
 #pragma unroll
     for (int j = 0; j < kFastPerThread; ++j) {
-      const uint32_t slot = b * kFastBatch + j * kFastThreads + tid;
-      idx[j] = slot < len ? pl[slot] : 0xFFFFFFFFu;
+      const uint32_t i = pos + j * kFastThreads + tid;
+      e_g[j] = 0u; e_hit[j] = 0u;
+      if (i < len) {
+        if (kMasked) { const uint2 e = cl[i]; e_g[j] = e.x; e_hit[j] = (e.y >> my_bit) & 1u; }
+        else { e_g[j] = pl[i]; e_hit[j] = 1u; }
+      }
     }
   };
-  auto stage = [&](int buf) {
+  int parity = 0;
+  auto fill = [&]() {  // until a full batch is pending or the list is exhausted
+    while (tail - head < (uint32_t)kFastBatch && pos < len) {
+      const unsigned h0 = __ballot_sync(0xffffffffu, e_hit[0] != 0u), h1 = __ballot_sync(0xffffffffu, e_hit[1] != 0u);
+      if (lane == 0) { s_cnt[parity][2 * warp] = (uint32_t)__popc(h0); s_cnt[parity][2 * warp + 1] = (uint32_t)__popc(h1); }
+      __syncthreads();
+      // list order of the round: (warp 0, first half) (warp 1, first half) (warp 0, second half) (warp 1, second half)
+      const uint32_t c00 = s_cnt[parity][0], c01 = s_cnt[parity][1], c10 = s_cnt[parity][2], c11 = s_cnt[parity][3];
+      if (e_hit[0]) s_ring[(tail + (warp ? c00 : 0u) + (uint32_t)__popc(h0 & lt_mask)) & (kRing - 1)] = e_g[0];
+      if (e_hit[1]) s_ring[(tail + c00 + c10 + (warp ? c01 : 0u) + (uint32_t)__popc(h1 & lt_mask)) & (kRing - 1)] = e_g[1];
+      tail += c00 + c01 + c10 + c11;
+      pos += (uint32_t)kFastBatch;
+      parity ^= 1;
+      prefetch();
+    }
+  };
+  // stage the ring's next `cnt` indices as records of buffer `buf`; list_pos = position of the batch in the tile's list
+  auto stage = [&](int buf, uint32_t cnt, uint32_t list_pos) {
 #pragma unroll
     for (int j = 0; j < kFastPerThread; ++j) {
-      float4* dst = &sm[buf][(j * kFastThreads + tid) * 3];
-      if (idx[j] != 0xFFFFFFFFu) {  // slots past the end of the list are never read: their survivor bit is 0
-        const float4* src = rec + 3 * (size_t)idx[j];
-        cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+      const uint32_t r = (uint32_t)(j * kFastThreads + tid);
+      if (r < cnt) {  // slots past the batch are never read: their survivor bit is 0
+        const uint32_t g = s_ring[(head + r) & (kRing - 1)];
+        const float4* s3 = rec + 3 * (size_t)g;
+        float4* dst = &sm[buf][r * 3];
+        cp_async16(dst, s3); cp_async16(dst + 1, s3 + 1); cp_async16(dst + 2, s3 + 2);
+        if (kAux && kMasked) out_list[list_pos + r] = g;
       }
     }
     cp_async_commit();
   };
-  // survivor masks of batch `b` (resident in buffer `buf`): record slot j*64 + tid is bit `lane` of word 2j + warp
-  auto build_masks = [&](int buf, uint32_t b) {
+  // survivor masks of the batch resident in buffer `buf`: record slot j*64 + tid is bit `lane` of word 2j + warp
+  auto build_masks = [&](int buf, uint32_t cnt) {
+    const bool dead0 = s_dead[0] != 0u, dead1 = s_dead[1] != 0u;  // written before the barrier at the loop top
 #pragma unroll
     for (int j = 0; j < kFastPerThread; ++j) {
-      const int r = j * kFastThreads + tid;
-      bool k0 = false, k1 = false;
-      if (b * kFastBatch + r < len) {
+      const uint32_t r = (uint32_t)(j * kFastThreads + tid);
+      bool k0 = r < cnt && !dead0, k1 = r < cnt && !dead1;  // a warp without live pixels reads no list
+      if (cull_on && r < cnt) {
         const float4 q0 = sm[buf][r * 3], q1 = sm[buf][r * 3 + 1];
         const float dxl = q0.x - rx1, dxh = q0.x - rx0;
-        k0 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry1, q0.y - ry0, cull);
-        k1 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry3, q0.y - ry2, cull);
+        if (k0) k0 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry1, q0.y - ry0, cull);
+        if (k1) k1 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry3, q0.y - ry2, cull);
       }
       const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
       if (lane == 0) { s_mask[buf][0][2 * j + warp] = m0; s_mask[buf][1][2 * j + warp] = m1; }
     }
   };
 
-  const uint32_t nb = (len + kFastBatch - 1) / kFastBatch;
-  if (nb > 0) { load_idx(0); stage(0); }
-  if (nb > 1) load_idx(1);
+  prefetch();
+  fill();
+  __syncthreads();  // ring (and the null records) visible
+  uint32_t cnt_cur = min(tail - head, (uint32_t)kFastBatch), consumed = 0;
+  stage(0, cnt_cur, 0u);
+  head += cnt_cur;
   bool warp_live = true;
-  for (uint32_t b = 0; b < nb; ++b) {
-    const int buf = (int)(b & 1);
+  for (uint32_t b = 0; cnt_cur > 0u; ++b) {
+    const int buf = (int)(b & 1u);
     cp_async_wait<0>();
-    // batch b visible to all; everyone is done reading the other buffer; stop when no pixel of the tile is live
+    // batch b visible to all; everyone is done with the other buffer and with the ring slots of batch b;
+    // stop when no pixel of the tile is live
     if (!__syncthreads_or(warp_live)) break;
-    if (b + 1 < nb) {
-      stage(buf ^ 1);
-      if (b + 2 < nb) load_idx(b + 2);
-    }
-    build_masks(buf, b);
-    __syncthreads();
+    fill();
+    build_masks(buf, cnt_cur);
+    __syncthreads();  // masks + ring visible
+    const uint32_t cnt_next = min(tail - head, (uint32_t)kFastBatch);
+    stage(buf ^ 1, cnt_next, consumed + cnt_cur);
+    head += cnt_next;
     if (warp_live) {
+      // compact this warp's survivor mask into a list of record slots
+      const uint4 mk = *reinterpret_cast<const uint4*>(s_mask[buf][warp]);
+      const uint32_t p1 = (uint32_t)__popc(mk.x), p2 = p1 + (uint32_t)__popc(mk.y), p3 = p2 + (uint32_t)__popc(mk.z);
+      const uint32_t total = p3 + (uint32_t)__popc(mk.w);
+      // list entries are the records' 16-bit shared-memory addresses: the loop below turns an entry into three LDS
+      // with one extract, no multiply, no base register
+      uint16_t* lst = s_list[warp];
+      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm[buf]);
+      if ((mk.x >> lane) & 1u) lst[__popc(mk.x & lt_mask)] = (uint16_t)(sbase + 48u * (uint32_t)lane);
+      if ((mk.y >> lane) & 1u) lst[p1 + __popc(mk.y & lt_mask)] = (uint16_t)(sbase + 48u * (uint32_t)(32 + lane));
+      if ((mk.z >> lane) & 1u) lst[p2 + __popc(mk.z & lt_mask)] = (uint16_t)(sbase + 48u * (uint32_t)(64 + lane));
+      if ((mk.w >> lane) & 1u) lst[p3 + __popc(mk.w & lt_mask)] = (uint16_t)(sbase + 48u * (uint32_t)(96 + lane));
+      if (lane < 4) lst[total + lane] = (uint16_t)(sbase + 48u * (uint32_t)kFastBatch);  // pad with the null record
+      __syncwarp();
+      const uint32_t nbase = consumed + 1u;  // kAux: list position + 1 of record slot 0
 #pragma unroll 1
-      for (int q = 0; q < kFastBatch / 32; ++q) {
-        uint32_t m = s_mask[buf][warp][q];
-        const float4* pq = sm[buf] + q * 32 * 3;
-        const uint32_t nbase = b * kFastBatch + q * 32 + 1;  // kAux: list position + 1 of bit 0
-        while (m) {
+      for (uint32_t j = 0; j < total; j += kFastUnroll) {
+        const uint2 four = *reinterpret_cast<const uint2*>(lst + j);
 #pragma unroll
-          for (int u = 0; u < kFastUnroll; ++u) {
-            if (m == 0u) break;
-            const int i = __ffs(m) - 1;
-            m &= m - 1u;
-            const float4* p = pq + i * 3;
-            const float4 q0 = p[0];  // mx, my, a, b
-            const float4 q1 = p[1];  // c, d, log2(op), r
-            const float2 q2 = *reinterpret_cast<const float2*>(p + 2);  // g, b
-            const float dx = q0.x - fx;
-            const float ta_ = __fmul_rn(dx, q0.z), tb_ = __fmul_rn(dx, q0.w);
-#define GSB_PIXEL_STEP(FY, T, LIVE, R, G, B, NC, TF)                                       \
-            {                                                                              \
-              const float dy = q0.y - FY;                                                  \
-              const float u0 = __fmaf_rn(dy, q1.x, ta_);                                   \
-              const float u1 = __fmaf_rn(dy, q1.y, tb_);                                   \
-              const float pw = __fadd_rn(__fmul_rn(u0, dx), __fmul_rn(u1, dy));            \
-              const float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z)); /* q1.z = log2(op) */ \
-              const float ta = T * al;                                                     \
-              T = T - ta;                                                                  \
-              LIVE = LIVE && (T >= minw);                                                  \
-              if (LIVE) { R = fmaf(ta, q1.w, R); G = fmaf(ta, q2.x, G); B = fmaf(ta, q2.y, B); } \
-              if (kAux) { if (LIVE) { NC = nbase + (uint32_t)i; TF = T; } }                \
-            }
-            GSB_PIXEL_STEP(fy0, T0, l0, r0, g0, b0, n0, tf0)
-            GSB_PIXEL_STEP(fy1, T1, l1, r1, g1, b1, n1, tf1)
-            GSB_PIXEL_STEP(fy2, T2, l2, r2, g2, b2, n2, tf2)
-            GSB_PIXEL_STEP(fy3, T3, l3, r3, g3, b3, n3, tf3)
-#undef GSB_PIXEL_STEP
-          }
-          if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) { warp_live = false; m = 0u; }
+        for (int u = 0; u < kFastUnroll; ++u) {
+          const uint32_t w2 = (u & 2) ? four.y : four.x;
+          const uint32_t addr = (u & 1) ? (w2 >> 16) : (w2 & 0xFFFFu);
+          const uint32_t i = (addr - sbase) / 48u;  // record slot (kAux only)
+          float4 q0, q1;  // mx, my, a, b | c, d, log2(op), r
+          float2 q2;      // g, b
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(addr));
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(addr));
+          asm("ld.shared.v2.f32 {%0,%1}, [%2+32];" : "=f"(q2.x), "=f"(q2.y) : "r"(addr));
+          const float dx = q0.x - fx;
+          const float ta_ = __fmul_rn(dx, q0.z), tb_ = __fmul_rn(dx, q0.w);
+          GSB_PIXEL_STEP(fy0, T0, l0, r0, g0, b0, n0, tf0)
+          GSB_PIXEL_STEP(fy1, T1, l1, r1, g1, b1, n1, tf1)
+          GSB_PIXEL_STEP(fy2, T2, l2, r2, g2, b2, n2, tf2)
+          GSB_PIXEL_STEP(fy3, T3, l3, r3, g3, b3, n3, tf3)
         }
-        if (!warp_live) break;
+        if (!__any_sync(0xffffffffu, l0 || l1 || l2 || l3)) {
+          warp_live = false;
+          if (lane == 0) s_dead[warp] = 1u;
+          break;
+        }
       }
     }
+    consumed += cnt_cur;
+    cnt_cur = cnt_next;
   }
   cp_async_wait<0>();
   if (px < a.width) {
@@ -353,7 +442,6 @@ composite_fast_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
   }
 }
 
-
 }  // namespace
 
 static float cull_threshold_log2(const GsbParams& prm) {
@@ -365,17 +453,21 @@ static float cull_threshold_log2(const GsbParams& prm) {
   return l < -127.f ? -127.f : l;
 }
 
-int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
-                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, const uint32_t* abort,
-                     cudaStream_t st) {
+int launch_composite(const TileSource& src, const float4* rec, float* image, FrameGeom geom, const GsbParams& prm,
+                     float* aux_t, uint32_t* aux_n, const uint32_t* abort, cudaStream_t st) {
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
   CompositeArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, prm.min_weight, prm.alpha_max,
                   cull_threshold_log2(prm)};
-  if (aux_t && aux_n)
-    composite_fast_kernel<true><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, aux_t, aux_n, abort, a);
+  const bool aux = aux_t && aux_n, masked = src.clist != nullptr;
+  if (aux && masked)
+    composite_fast_kernel<true, true><<<tiles, kFastThreads, 0, st>>>(src, rec, image, aux_t, aux_n, abort, a);
+  else if (aux)
+    composite_fast_kernel<true, false><<<tiles, kFastThreads, 0, st>>>(src, rec, image, aux_t, aux_n, abort, a);
+  else if (masked)
+    composite_fast_kernel<false, true><<<tiles, kFastThreads, 0, st>>>(src, rec, image, nullptr, nullptr, abort, a);
   else
-    composite_fast_kernel<false><<<tiles, kFastThreads, 0, st>>>(ranges, payload, rec, image, nullptr, nullptr, abort, a);
+    composite_fast_kernel<false, false><<<tiles, kFastThreads, 0, st>>>(src, rec, image, nullptr, nullptr, abort, a);
   return (int)cudaGetLastError();
 }
 

@@ -102,21 +102,13 @@ CtlLayout ctl_layout(FrameGeom g, SuperGeom sg, int64_t n_rows, size_t dsort_wor
   return L;
 }
 
-// Super-tile shape of SPLIT mode: start at 8 x 4 tiles and double the smaller side until the frame has at most
-// `max_supers` super-tiles (256: ONE radix pass over their ids; 1080p -> 15 x 17 = 255 super-tiles of 8 x 4 tiles,
-// 4K -> 15 x 17 of 16 x 8).  lw = lh = 0 switches the second level off (one key per tile instance).
-SuperGeom choose_super(FrameGeom g, int lw, int lh, int max_supers) {
+// Super-tile shape of SPLIT mode: 2^lw x 2^lh tiles with lw + lh <= 5, so that "which tiles of the super-tile does
+// this rect cover" is ONE 32-bit mask (8 x 4 by default: 255 super-tiles at 1080p -> one radix pass over their
+// ids; 1 020 at 4K -> two).  lw = lh = 0 switches the second level off (one key per tile instance).
+SuperGeom choose_super(FrameGeom g, int lw, int lh) {
   SuperGeom s{lw, lh, 0, 0};
-  auto dims = [&] {
-    s.nx = (g.tiles_x + (1 << s.lw) - 1) >> s.lw;
-    s.ny = (g.tiles_y + (1 << s.lh) - 1) >> s.lh;
-  };
-  dims();
-  if (lw == 0 && lh == 0) return s;
-  while ((int64_t)s.nx * s.ny > max_supers && s.lw + s.lh < 30) {
-    if (s.lh < s.lw) ++s.lh; else ++s.lw;
-    dims();
-  }
+  s.nx = (g.tiles_x + (1 << s.lw) - 1) >> s.lw;
+  s.ny = (g.tiles_y + (1 << s.lh) - 1) >> s.lh;
   return s;
 }
 
@@ -140,7 +132,7 @@ struct GsbContext {
   DevBuf aux_t, aux_n, grad2d, grad_stage;
   DevBuf host_stage[2];
   bool allow_keys32 = true;
-  int super_lw = 3, super_lh = 2, super_max = 256;
+  int super_lw = 3, super_lh = 2;
   bool frame_projected = false;  // last frame came from render_device: last_cam / last_prm describe its projection
   GsbCamera last_cam{};
   GsbParams last_prm{};
@@ -164,6 +156,8 @@ struct GsbContext {
   bool sorted_in_a = true;
   bool emitted_valid = false;
   bool keys_materialized = true;  // false in SPLIT mode: sorted 64-bit keys are rebuilt on demand (debug)
+  bool lists_materialized = true; // false after a two-level SPLIT frame: per-tile lists exist only as super-tile lists
+  SuperGeom last_sg{0, 0, 0, 0};
   bool order_in_a = true;
   bool have_order = false;
   int64_t frame_rows = 0;  // rows of the per-Gaussian arrays of the last frame (N, or M for gsb_render_image)
@@ -354,31 +348,36 @@ int bin_full(GsbContext* c, int64_t n_rows, FrameGeom geom, uint32_t* ctl, const
 struct SplitPlan {
   SuperGeom sg;
   bool two_level, keys32;
+  // two_level frames store per-tile lists only when somebody reads them as arrays: the gradient pass (the
+  // compositing kernel then writes what it consumes: payload_side) or the REF_CU kernel (expand_in_stream)
+  bool payload_side, expand_in_stream;
   int rank_bits, sbits;
   int64_t cap_k, cap_ks;
+  bool need_payload() const { return !two_level || payload_side || expand_in_stream; }
 };
 
 int split_capacities(GsbContext* c, int64_t n_rows, const SplitPlan& sp, int64_t need_k, int64_t need_ks) {
-  // payload: 4 B per tile instance; super-tile level: one key ping-pong + the sorted indices
+  // payload: 4 B per tile instance (if stored at all); super-tile level: one key ping-pong + 8 B list entries
   const size_t kb = sp.keys32 ? 4 : 8;
   if (need_k < 16 * n_rows) need_k = 16 * n_rows;  // first guess of a fresh context
   if (!sp.two_level) need_ks = need_k;
   else if (need_ks < 4 * n_rows) need_ks = 4 * n_rows;
-  GSB_TRY(c->vals_a.ensure((size_t)need_k * 4 + 16));
+  if (sp.need_payload()) GSB_TRY(c->vals_a.ensure((size_t)need_k * 4 + 16));
   GSB_TRY(c->ckeys_a.ensure((size_t)need_ks * kb + 16));
   GSB_TRY(c->ckeys_b.ensure((size_t)need_ks * kb + 16));
-  if (sp.two_level) GSB_TRY(c->cvals.ensure((size_t)need_ks * 4 + 16));
+  if (sp.two_level) GSB_TRY(c->cvals.ensure((size_t)need_ks * 8 + 16));
   return GSB_OK;
 }
 
-SplitPlan make_split_plan(GsbContext* c, int64_t n_rows, FrameGeom geom, SuperGeom sg) {
+SplitPlan make_split_plan(GsbContext* c, int64_t n_rows, SuperGeom sg, bool payload_side, bool expand_in_stream) {
   SplitPlan sp;
   sp.sg = sg;
   sp.two_level = sg.lw + sg.lh > 0;
+  sp.payload_side = sp.two_level && payload_side;
+  sp.expand_in_stream = sp.two_level && expand_in_stream;
   sp.sbits = ceil_log2((int64_t)sg.nx * sg.ny);
   sp.rank_bits = ceil_log2(n_rows);
   sp.keys32 = c->allow_keys32 && sp.sbits + sp.rank_bits <= 32;
-  (void)geom;
   sp.cap_k = sp.cap_ks = 0;
   return sp;
 }
@@ -386,12 +385,12 @@ SplitPlan make_split_plan(GsbContext* c, int64_t n_rows, FrameGeom geom, SuperGe
 void read_capacities(GsbContext* c, SplitPlan& sp) {
   const size_t kb = sp.keys32 ? 4 : 8;
   const int64_t lim = ((int64_t)1 << 32) - 2;  // positions are u32
-  int64_t ck = (int64_t)((c->vals_a.cap - 16) / 4);
+  int64_t ck = sp.need_payload() ? (int64_t)((c->vals_a.cap - 16) / 4) : lim;
   int64_t cks = (int64_t)((c->ckeys_a.cap - 16) / kb);
   const int64_t cks_b = (int64_t)((c->ckeys_b.cap - 16) / kb);
   if (cks_b < cks) cks = cks_b;
   if (sp.two_level) {
-    const int64_t cv = (int64_t)((c->cvals.cap - 16) / 4);
+    const int64_t cv = (int64_t)((c->cvals.cap - 16) / 8);
     if (cv < cks) cks = cv;
   } else {
     if (ck < cks) cks = ck; else ck = cks;
@@ -415,6 +414,7 @@ int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const 
     plan.gather_table = perm;  // nullptr (pre-sorted rows): the position IS the row
     plan.n_dev = ctl + kCtlKs;
     plan.abort = abort;
+    if (sp.two_level) { plan.entry_rect = c->rect.as<ushort4>(); plan.entry_lw = sp.sg.lw; plan.entry_lh = sp.sg.lh; plan.entry_snx = sp.sg.nx; }
     GSB_TRY(c->control2.ensure(plan.control_words * 4));
     GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
     GSB_CUDA_TRY((cudaError_t)launch_emit_coarse(c->offsets.as<uint32_t>(), perm, ctl + kCtlKs, n_rows, v_limit, abort,
@@ -430,6 +430,7 @@ int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const 
     plan.keys_only = 1;
     plan.n_dev = ctl + kCtlKs;
     plan.abort = abort;
+    if (sp.two_level) { plan.entry_rect = c->rect.as<ushort4>(); plan.entry_lw = sp.sg.lw; plan.entry_lh = sp.sg.lh; plan.entry_snx = sp.sg.nx; }
     GSB_TRY(c->control2.ensure(plan.control_words * 4));
     GSB_CUDA_TRY(cudaMemsetAsync(c->control2.p, 0, plan.control_words * 4, st));
     GSB_CUDA_TRY((cudaError_t)launch_emit_coarse(c->offsets.as<uint32_t>(), perm, ctl + kCtlKs, n_rows, v_limit, abort,
@@ -442,13 +443,15 @@ int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const 
     passes = plan.passes;
   }
   tm.mark(GSB_STAGE_SORT);
-  if (sp.two_level) {
-    GSB_CUDA_TRY((cudaError_t)launch_expand(c->ranges_s.as<uint2>(), c->cvals.as<uint32_t>(), c->rect.as<ushort4>(),
-                                            c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), geom, sp.sg, abort, st));
+  if (sp.expand_in_stream) {
+    GSB_CUDA_TRY((cudaError_t)launch_expand(c->ranges_s.as<uint2>(), c->cvals.as<uint2>(), c->ranges.as<uint2>(),
+                                            c->vals_a.as<uint32_t>(), geom, sp.sg, abort, st));
     ++*launches;
     tm.mark(GSB_STAGE_EXPAND);
   }
   c->keys_materialized = false;
+  c->lists_materialized = !sp.two_level || sp.expand_in_stream;
+  c->last_sg = sp.sg;
   c->sorted_in_a = true;
   c->emitted_valid = false;
   c->info.sort_passes = passes;
@@ -473,10 +476,22 @@ void finish_times(GsbContext* c, cudaStream_t st, bool on) {
 // What follows the per-Gaussian records in SPLIT mode, shared by gsb_render (projected rows, depth order in `perm`)
 // and gsb_render_image (the caller's pre-sorted rows): scan -> [emit, sort, expand, composite] queued from
 // capacities -> counts from the mailbox -> on overflow grow and queue the bracketed tail once more.
+TileSource tile_source(GsbContext* c, const SplitPlan* sp) {
+  TileSource src{c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), nullptr, nullptr, nullptr, 1, 0, 0};
+  if (sp && sp->two_level && !sp->expand_in_stream) {
+    src.payload = nullptr;
+    src.ranges_s = c->ranges_s.as<uint2>();
+    src.clist = c->cvals.as<uint2>();
+    src.payload_out = sp->payload_side ? c->vals_a.as<uint32_t>() : nullptr;
+    src.snx = sp->sg.nx; src.lw = sp->sg.lw; src.lh = sp->sg.lh;
+  }
+  return src;
+}
+
 template <typename CompositeFn>
 int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sorted_by_visibility, FrameGeom geom,
-              SuperGeom sg, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm, int* launches,
-              CompositeFn&& queue_composite) {
+              SuperGeom sg, bool payload_side, bool expand_in_stream, uint32_t* ctl, const CtlLayout& L, cudaStream_t st,
+              StageTimer& tm, int* launches, CompositeFn&& queue_composite) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
   if (tiles <= 0 || n_rows <= 0) {  // nothing to bin; the compositing launcher handles an empty grid itself
     Counts cn;
@@ -489,9 +504,10 @@ int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sor
       GSB_TRY(c->vals_a.ensure(16));
     }
     c->keys_materialized = false;
+    c->lists_materialized = true;
     c->sorted_in_a = true;
     c->emitted_valid = false;
-    return queue_composite(nullptr);
+    return queue_composite(tile_source(c, nullptr), nullptr);
   }
   const uint32_t* v_limit = rows_sorted_by_visibility ? ctl + kCtlVisible : nullptr;
   GSB_TRY(c->offsets.ensure((size_t)n_rows * 4 + 4));
@@ -500,10 +516,10 @@ int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sor
   ++*launches;
   tm.mark(GSB_STAGE_SCAN);
   GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // ranges / super-tile histograms are inputs of what follows
-  SplitPlan sp = make_split_plan(c, n_rows, geom, sg);
+  SplitPlan sp = make_split_plan(c, n_rows, sg, payload_side, expand_in_stream);
   read_capacities(c, sp);  // the capacities tile_stats_kernel was given (launch_stats_async ran with the same values)
   GSB_TRY(queue_split_tail(c, n_rows, perm, v_limit, geom, sp, ctl, L, st, tm, launches));
-  GSB_TRY(queue_composite(ctl + kCtlAbort));
+  GSB_TRY(queue_composite(tile_source(c, &sp), ctl + kCtlAbort));
   Counts cn;
   GSB_TRY(wait_counts(c, tiles, ctl, st, &cn));
   if (cn.k >= ((int64_t)1 << 32) - 1 || cn.ks >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // positions are u32
@@ -519,15 +535,16 @@ int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sor
     if (cn.k > sp.cap_k || cn.ks > sp.cap_ks) return GSB_E_INTERNAL;
     GSB_CUDA_TRY(cudaMemsetAsync(ctl + kCtlAbort, 0, 4, st));
     GSB_TRY(queue_split_tail(c, n_rows, perm, v_limit, geom, sp, ctl, L, st, tm, launches));
-    GSB_TRY(queue_composite(ctl + kCtlAbort));
+    GSB_TRY(queue_composite(tile_source(c, &sp), ctl + kCtlAbort));
   }
   return GSB_OK;
 }
 
 // capacities the stats kernel is told for this frame (must equal what run_split reads back: both derive them from
 // the same buffers, and nothing reallocates in between)
-int prepare_split(GsbContext* c, int64_t n_rows, FrameGeom geom, SuperGeom sg, uint64_t* cap_k, uint64_t* cap_ks) {
-  SplitPlan sp = make_split_plan(c, n_rows, geom, sg);
+int prepare_split(GsbContext* c, int64_t n_rows, SuperGeom sg, bool payload_side, bool expand_in_stream, uint64_t* cap_k,
+                  uint64_t* cap_ks) {
+  SplitPlan sp = make_split_plan(c, n_rows, sg, payload_side, expand_in_stream);
   GSB_TRY(split_capacities(c, n_rows, sp, 0, 0));  // no-op once the buffers exist
   read_capacities(c, sp);
   *cap_k = (uint64_t)sp.cap_k;
@@ -547,7 +564,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
                  tile_grid_dim(cam->height, kTile, prm->full_cover)};
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
   const bool split = prm->sort_mode != GSB_SORT_FULL;  // AUTO = SPLIT
-  const SuperGeom sg = split ? choose_super(geom, c->super_lw, c->super_lh, c->super_max) : SuperGeom{0, 0, geom.tiles_x, geom.tiles_y};
+  const SuperGeom sg = split ? choose_super(geom, c->super_lw, c->super_lh) : SuperGeom{0, 0, geom.tiles_x, geom.tiles_y};
   const bool two_level = split && sg.lw + sg.lh > 0;
   int launches = 0;
   begin_frame(c);
@@ -563,7 +580,8 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   const CtlLayout L = ctl_layout(geom, sg, n, split ? dplan.control_words : 0);
   GSB_TRY(c->control.ensure(L.total * 4));
   uint64_t cap_k = ~0ull, cap_ks = ~0ull;  // FULL: the host sizes everything after it has seen K
-  if (split && n > 0 && tiles > 0) GSB_TRY(prepare_split(c, n, geom, sg, &cap_k, &cap_ks));
+  const bool payload_side = prm->save_for_backward != 0;  // the gradient pass walks per-tile lists as arrays
+  if (split && n > 0 && tiles > 0) GSB_TRY(prepare_split(c, n, sg, payload_side, false, &cap_k, &cap_ks));
   GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* ctl = c->control.as<uint32_t>();
 
@@ -586,13 +604,12 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
     aux_t = c->aux_t.as<float>();
     aux_n = c->aux_n.as<uint32_t>();
   }
-  auto queue_composite = [&](const uint32_t* abort) -> int {
+  auto queue_composite = [&](const TileSource& src, const uint32_t* abort) -> int {
     if (!prm->full_cover) {  // pixels outside the reference tile grid stay 0 (splat/gaussian_scene.py:206)
       GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, (size_t)cam->width * cam->height * 3 * sizeof(float), st));
       if (aux_n) GSB_CUDA_TRY(cudaMemsetAsync(aux_n, 0, (size_t)cam->width * cam->height * 4, st));  // nothing blended there
     }
-    GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), c->rec.as<float4>(),
-                                               dev_image, geom, *prm, aux_t, aux_n, abort, st));
+    GSB_CUDA_TRY((cudaError_t)launch_composite(src, c->rec.as<float4>(), dev_image, geom, *prm, aux_t, aux_n, abort, st));
     if (tiles > 0) ++launches;
     tm.mark(GSB_STAGE_COMPOSITE);
     return GSB_OK;
@@ -607,7 +624,8 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
       perm = c->order_in_a ? c->ord_vals_a.as<uint32_t>() : c->ord_vals_b.as<uint32_t>();
       tm.mark(GSB_STAGE_DEPTH_SORT);
     }
-    GSB_TRY(run_split(c, n, perm, /*rows_sorted_by_visibility=*/true, geom, sg, ctl, L, st, tm, &launches, queue_composite));
+    GSB_TRY(run_split(c, n, perm, /*rows_sorted_by_visibility=*/true, geom, sg, payload_side, false, ctl, L, st, tm,
+                      &launches, queue_composite));
   } else {
     if (n > 0 && tiles > 0) {
       GSB_TRY(bin_full(c, n, geom, ctl, L, st, tm, &launches));
@@ -624,13 +642,14 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
       c->keys_materialized = false;
       c->emitted_valid = false;
     }
+    c->lists_materialized = true;
     if (!c->sorted_in_a) {  // the compositing launcher above reads vals_a: an odd pass count left the order in vals_b
       std::swap(c->vals_a.p, c->vals_b.p); std::swap(c->vals_a.cap, c->vals_b.cap);
       std::swap(c->keys_a.p, c->keys_b.p); std::swap(c->keys_a.cap, c->keys_b.cap);
       c->sorted_in_a = true;
       c->emitted_valid = false;
     }
-    GSB_TRY(queue_composite(nullptr));
+    GSB_TRY(queue_composite(tile_source(c, nullptr), nullptr));
   }
   c->info.kernel_launches = launches;
   c->frame_rows = n;
@@ -710,12 +729,10 @@ int gsb_create(GsbContext** out, int device) {
     e = std::getenv("GSB_SUPER");                         // "lw,lh": log2 tiles per super-tile; "0,0": one level
     if (e) {
       int lw = 3, lh = 2;
-      if (std::sscanf(e, "%d,%d", &lw, &lh) == 2 && lw >= 0 && lh >= 0 && lw <= 8 && lh <= 8 && (lw + lh == 0 || lw + lh >= 4)) {
+      if (std::sscanf(e, "%d,%d", &lw, &lh) == 2 && lw >= 0 && lh >= 0 && lw + lh <= 5) {
         c->super_lw = lw; c->super_lh = lh;
       }
     }
-    e = std::getenv("GSB_SUPER_MAX");                     // most super-tiles per frame (256 = one radix pass)
-    if (e && std::atoi(e) >= 1) c->super_max = std::atoi(e);
   }
   if (cudaHostAlloc((void**)&c->pinned, 64, cudaHostAllocMapped) != cudaSuccess) { delete c; return GSB_E_ALLOC; }
   std::memset(c->pinned, 0, 64);
@@ -1010,7 +1027,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   const int cover = cu ? 1 : prm.full_cover;  // render.cu covers every pixel (:119-124)
   FrameGeom geom{W, H, tile_grid_dim(W, kTile, cover), tile_grid_dim(H, kTile, cover)};
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
-  const SuperGeom sg = choose_super(geom, c->super_lw, c->super_lh, c->super_max);
+  const SuperGeom sg = choose_super(geom, c->super_lw, c->super_lh);
   const bool two_level = sg.lw + sg.lh > 0;
   begin_frame(c);  // overwrites rec / ranges / payload with M-row data: a frame saved for the backward pass is gone
   c->info.n = m; c->info.tiles_x = geom.tiles_x; c->info.tiles_y = geom.tiles_y;
@@ -1042,7 +1059,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   const CtlLayout L = ctl_layout(geom, sg, m, 0);
   GSB_TRY(c->control.ensure(L.total * 4));
   uint64_t cap_k = ~0ull, cap_ks = ~0ull;
-  if (m > 0 && tiles > 0) GSB_TRY(prepare_split(c, m, geom, sg, &cap_k, &cap_ks));
+  if (m > 0 && tiles > 0) GSB_TRY(prepare_split(c, m, sg, false, /*expand_in_stream=*/cu, &cap_k, &cap_ks));
   GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* hdr = c->control.as<uint32_t>();
   tm.start();
@@ -1059,19 +1076,19 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   const size_t bytes = (size_t)W * H * 3 * sizeof(float);
   const bool host_out = !is_device_pointer(out_image);
   if (host_out) { GSB_TRY(c->image.ensure(bytes)); dev_image = c->image.as<float>(); }
-  auto queue_composite = [&](const uint32_t* abort) -> int {
+  auto queue_composite = [&](const TileSource& src, const uint32_t* abort) -> int {
     if (!cover) GSB_CUDA_TRY(cudaMemsetAsync(dev_image, 0, bytes, st));
-    if (cu)
+    if (cu)  // the REF_CU kernel walks materialised per-tile lists (expand_in_stream)
       GSB_CUDA_TRY((cudaError_t)launch_composite_cu(c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), c->rec.as<float4>(),
                                                     c->bbox.as<float4>(), dev_image, geom, prm, abort, st));
     else
-      GSB_CUDA_TRY((cudaError_t)launch_composite(c->ranges.as<uint2>(), c->vals_a.as<uint32_t>(), c->rec.as<float4>(),
-                                                 dev_image, geom, prm, nullptr, nullptr, abort, st));
+      GSB_CUDA_TRY((cudaError_t)launch_composite(src, c->rec.as<float4>(), dev_image, geom, prm, nullptr, nullptr, abort, st));
     if (tiles > 0) ++launches;
     tm.mark(GSB_STAGE_COMPOSITE);
     return GSB_OK;
   };
-  GSB_TRY(run_split(c, m, nullptr, /*rows_sorted_by_visibility=*/false, geom, sg, hdr, L, st, tm, &launches, queue_composite));
+  GSB_TRY(run_split(c, m, nullptr, /*rows_sorted_by_visibility=*/false, geom, sg, false, /*expand_in_stream=*/cu, hdr, L, st,
+                    tm, &launches, queue_composite));
   c->info.m_in_view = m;
   if (host_out) GSB_CUDA_TRY(cudaMemcpyAsync(out_image, dev_image, bytes, cudaMemcpyDeviceToHost, st));
   c->info.kernel_launches = launches;
@@ -1167,6 +1184,17 @@ int gsb_debug_sorted_keys(GsbContext* c, uint64_t* keys, uint32_t* payload) {
   GSB_CUDA_TRY(cudaDeviceSynchronize());  // legacy-stream getter: order it after the frame's stream
   const size_t k = (size_t)c->info.k_instances;
   if (k == 0) return GSB_OK;
+  if (!c->lists_materialized) {
+    // two-level SPLIT frames keep the per-tile lists implicit (super-tile lists + tile masks; the compositing kernel
+    // filters them on the fly): write them out now, with the same filter, as one array per tile
+    GSB_TRY(c->vals_a.ensure(k * 4 + 16));
+    FrameGeom geom{0, 0, c->info.tiles_x, c->info.tiles_y};
+    GSB_CUDA_TRY((cudaError_t)launch_expand(c->ranges_s.as<uint2>(), c->cvals.as<uint2>(), c->ranges.as<uint2>(),
+                                            c->vals_a.as<uint32_t>(), geom, c->last_sg, nullptr, 0));
+    GSB_CUDA_TRY(cudaDeviceSynchronize());
+    c->lists_materialized = true;
+    c->sorted_in_a = true;
+  }
   const uint32_t* sv = c->sorted_in_a ? c->vals_a.as<uint32_t>() : c->vals_b.as<uint32_t>();
   if (keys) {
     if (c->keys_materialized) {

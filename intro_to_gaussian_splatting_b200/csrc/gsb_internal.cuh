@@ -112,9 +112,10 @@ int launch_emit(const uint32_t* offsets, const uint32_t* perm, const uint32_t* t
 int launch_emit_coarse(const uint32_t* offsets, const uint32_t* perm, const uint32_t* total, int64_t n,
                        const uint32_t* v_limit, const uint32_t* abort, int64_t capacity, const ushort4* rect,
                        SuperGeom sg, int rank_bits, void* keys, cudaStream_t st);
-// per-tile lists from per-super-tile lists (stable compaction; the tile starts come from `ranges`)
-int launch_expand(const uint2* ranges_s, const uint32_t* cpay, const ushort4* rect, const uint2* ranges,
-                  uint32_t* payload, FrameGeom geom, SuperGeom sg, const uint32_t* abort, cudaStream_t st);
+// per-tile lists from per-super-tile lists of {Gaussian index, tile mask} entries (stable compaction; the tile
+// starts come from `ranges`).  On demand only: the compositing kernel filters the super-tile lists itself.
+int launch_expand(const uint2* ranges_s, const uint2* clist, const uint2* ranges, uint32_t* payload, FrameGeom geom,
+                  SuperGeom sg, const uint32_t* abort, cudaStream_t st);
 // debug only: sorted keys tile<<32 | depth bits from ranges + sorted payload (SPLIT mode never stores them)
 int launch_rebuild_keys(const uint2* ranges, int tiles, const uint32_t* payload, const uint32_t* depth_key,
                         uint64_t* keys, cudaStream_t st);
@@ -131,6 +132,11 @@ struct SortPlan {
   const uint32_t* n_dev;  // optional: the key count lives on the device (u32); `n` is then the CAPACITY the grid and
                           // the status words are sized for, tiles past *n_dev return at once
   const uint32_t* abort;  // optional: nothing runs when *abort != 0
+  // keys_only, optional: the last pass writes super-tile list entries {Gaussian index, tile mask} (uint2, to the vals
+  // buffer of its destination side) instead of bare indices; the mask comes from entry_rect[index] and the
+  // super-tile id in the key's sorted bits (super-tiles of 2^entry_lw x 2^entry_lh tiles, entry_snx per row)
+  const ushort4* entry_rect;
+  int entry_lw, entry_lh, entry_snx;
   int64_t n;
   int64_t tiles;          // onesweep tiles per pass
   size_t control_words;   // u32 words of control memory (tickets + look-back status), zeroed by the caller
@@ -150,12 +156,24 @@ int launch_sort(const SortPlan& plan, const KeyT* keys_src, const uint32_t* vals
                 KeyT* keys_b, uint32_t* vals_b, const uint32_t* hist, uint32_t* control, bool* result_in_a,
                 int* launches, cudaStream_t st);
 
+// Where the compositing kernel gets a tile's list from.  clist == nullptr: a materialised per-tile payload array
+// (`payload` sliced by `ranges`; FULL mode, one-level SPLIT).  clist != nullptr: the tile filters its super-tile's
+// list of {Gaussian index, tile mask} entries (`clist` sliced by `ranges_s`) on the fly; with save_for_backward it
+// also writes the list it consumes to payload_out[ranges[tile].x ..] for the gradient pass.
+struct TileSource {
+  const uint2* ranges;
+  const uint32_t* payload;
+  const uint2* ranges_s;
+  const uint2* clist;
+  uint32_t* payload_out;
+  int snx, lw, lh;
+};
+
 // aux_t / aux_n (both or neither; save_for_backward): per pixel, transmittance after the last blended Gaussian
-// and the number of blended Gaussians (the prefix [0, n) of the tile's list)
-// abort (optional): device flag; the kernel returns at once when it is set (see kCtlAbort)
-int launch_composite(const uint2* ranges, const uint32_t* payload, const float4* rec, float* image,
-                     FrameGeom geom, const GsbParams& prm, float* aux_t, uint32_t* aux_n, const uint32_t* abort,
-                     cudaStream_t st);
+// and the length of the list prefix that reached the pixel.  abort (optional): device flag; the kernel returns at
+// once when it is set (see kCtlAbort).
+int launch_composite(const TileSource& src, const float4* rec, float* image, FrameGeom geom, const GsbParams& prm,
+                     float* aux_t, uint32_t* aux_n, const uint32_t* abort, cudaStream_t st);
 
 // ---- backward pass (backward.cu) ----
 // grad2d: 12 zeroed floats per Gaussian row: d mean x,y | d a, d (b+c), d d (a b; c d = -0.5 inverse covariance) |

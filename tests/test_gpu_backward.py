@@ -260,7 +260,7 @@ def test_edge_cases():
     only = torch.empty((n, 3), device="cuda")
     lib = _lib.load()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.gsb_render_backward(r._h, C.byref(cam3), C.byref(prm3), C.c_void_p(torch.from_numpy(gi2).cuda().data_ptr()),
+    _lib.check(lib.gsb_render_backward(r._h, C.byref(cam3), C.byref(prm3), 0, C.c_void_p(torch.from_numpy(gi2).cuda().data_ptr()),
                                        None, None, None, C.c_void_p(only.data_ptr()), None, st))
     torch.cuda.synchronize()
     assert torch.allclose(only, got["colors"], rtol=1e-4, atol=1e-7)

@@ -59,7 +59,7 @@ def test_random_scene(rast, seed):
                      tvec=(float(rng.normal() * 0.5), float(rng.normal() * 0.5), float(rng.uniform(-1, 6))), seed=seed)
     sc, images, _ = scene_and_images(spec)
     arrs = [sc.xyz, sc.scales, sc.quats, (sc.rgb255 / 256).float(), sc.opacity_logit]
-    prm = _lib.default_params(full_cover=int(rng.integers(0, 2)), sort_mode=int(rng.integers(1, 4)))
+    prm = _lib.default_params(full_cover=int(rng.integers(0, 2)), sort_mode=int(rng.integers(1, 3)))
     _compare(rast, images[1].pack(), prm, arrs)
 
 

@@ -20,18 +20,23 @@ ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--sort-mode", default="auto")
 ap.add_argument("--full-cover", type=int, default=1)
 ap.add_argument("--stage-times", type=int, default=0)
+ap.add_argument("--cull-alpha", type=float, default=None)
+ap.add_argument("--views", default="", help="comma-separated orbit view numbers to render instead of 0..frames-1")
 a = ap.parse_args()
-sc = make_scene(CONFIGS[a.config], n_views=max(a.frames, 1))
+views = [int(v) for v in a.views.split(",") if v] or list(range(max(a.frames, 1)))
+sc = make_scene(CONFIGS[a.config], n_views=max(views) + 1)
 d = tempfile.mkdtemp()
 write_colmap_text(sc, d)
 cams, imgs = read_camera_file(d), read_image_file(d)
 packed = [GaussianImage(cams[imgs[i].camera_id], imgs[i]).pack() for i in sorted(imgs)]
 r = Rasterizer(0)
 r.upload(sc.xyz.cuda(), sc.scales.cuda(), sc.quats.cuda(), (sc.rgb255 / 256).float().cuda(), sc.opacity_logit.cuda())
-mode = {"auto": 0, "full": 1, "split": 2, "binned": 3}[a.sort_mode]
+mode = {"auto": 0, "full": 1, "split": 2}[a.sort_mode]
 prm = _lib.default_params(full_cover=a.full_cover, sort_mode=mode, collect_stage_times=a.stage_times)
+if a.cull_alpha is not None:
+    prm.cull_alpha = a.cull_alpha
 img = torch.empty((sc.spec.height, sc.spec.width, 3), device="cuda")
-for f in range(a.frames):
+for f in views:
     r.render(packed[f], prm, out=img)
     torch.cuda.synchronize()
     info = r.frame_info()
