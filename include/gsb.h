@@ -122,6 +122,9 @@ typedef struct GsbFrameInfo {
   int64_t k_sorted;    /* keys those passes moved: K (FULL) or the number of super-tile instances (SPLIT) */
   int64_t frame_id;    /* increases with every frame this context renders; gsb_render_backward checks it */
   int32_t super_w, super_h; /* SPLIT: tiles per super-tile (1 x 1: single-level binning) */
+  int64_t v_with_tiles; /* in-view Gaussians whose tile rect is not empty (the rows the binning stages touch) */
+  int32_t tail_requeued; /* 1: a count outgrew the capacities the frame was queued with and its tail was queued twice */
+  int32_t reserved;
 } GsbFrameInfo;
 
 typedef struct GsbContext GsbContext;

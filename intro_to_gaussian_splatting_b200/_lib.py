@@ -80,6 +80,9 @@ class GsbFrameInfo(C.Structure):
         ("frame_id", C.c_int64),
         ("super_w", C.c_int32),
         ("super_h", C.c_int32),
+        ("v_with_tiles", C.c_int64),
+        ("tail_requeued", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

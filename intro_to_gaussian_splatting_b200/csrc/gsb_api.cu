@@ -311,6 +311,7 @@ int bin_full(GsbContext* c, int64_t n_rows, FrameGeom geom, uint32_t* ctl, const
   if (tiles > 0) GSB_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_stats, 0));  // tile histograms are inputs of the sort
   if (cn.k >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // payload positions and ranges are u32
   c->info.m_in_view = cn.m;
+  c->info.v_with_tiles = cn.v;
   c->info.k_instances = cn.k;
   c->info.k_sorted = cn.k;
   const int64_t k = cn.k;
@@ -524,9 +525,11 @@ int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sor
   GSB_TRY(wait_counts(c, tiles, ctl, st, &cn));
   if (cn.k >= ((int64_t)1 << 32) - 1 || cn.ks >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // positions are u32
   c->info.m_in_view = cn.m;
+  c->info.v_with_tiles = rows_sorted_by_visibility ? cn.v : 0;
   c->info.k_instances = cn.k;
   c->info.k_sorted = cn.ks;
   if (cn.abort) {
+    c->info.tail_requeued = 1;
     // a count outgrew its buffer: none of the tail kernels touched anything.  Grow (cudaFree drains the device),
     // clear the flag and queue the tail once more; the projection, depth order, ranges and offsets stand.
     ++c->tail_reruns;

@@ -26,7 +26,7 @@ from .gaussians import Gaussians
 from .image import GaussianImage
 from .rasterizer import Rasterizer, ViewRenderer
 from .schema import PreprocessedScene
-from .utils import read_camera_file, read_image_file
+from .utils import compute_2d_covariance, read_camera_file, read_image_file
 
 
 class _ExtShim:
@@ -91,14 +91,58 @@ class GaussianScene(nn.Module):
 
     # ---- the reference API ----------------------------------------------------------------------
     def render_points_image(self, image_idx: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Pixel centres + colours of the in-view Gaussians in index order (debug scatter,
-        splat/gaussian_scene.py:44-51): served from the projection kernel's records."""
-        rast = self._sync_gaussians()
-        # rows come back depth-sorted; undo that to return Gaussian-index order like the reference
-        pp, src = rast.preprocess(self.images[image_idx].pack(), self._params(16), with_source_index=True)
-        inv = torch.argsort(src.long())
-        pts = torch.cat([pp.points_xy[inv], pp.depths[inv].unsqueeze(1)], dim=1)
-        return pts, pp.colors[inv]
+        """(pixel x, pixel y, NDC z) + colours of the in-view Gaussians in index order: the debug scatter of
+        splat/gaussian_scene.py:44-51, same delegation to the image as there."""
+        return self.images[image_idx].project_point_to_camera_perspective_projection(self.gaussians.points,
+                                                                                      self.gaussians.colors)
+
+    def get_2d_covariance(self, image_idx: int, points: torch.Tensor, covariance_3d: torch.Tensor) -> torch.Tensor:
+        """(M,2,2) EWA covariance of `points` for this view (splat/gaussian_scene.py:53-68).  A torch helper for
+        callers of the public method; frames get theirs from csrc/project.cu."""
+        im = self.images[image_idx]
+        return compute_2d_covariance(points=points, extrinsic_matrix=im.world2view.to(points.device),
+                                     covariance_3d=covariance_3d, tan_fovX=im.tan_fovX.to(points.device),
+                                     tan_fovY=im.tan_fovY.to(points.device), focal_x=im.f_x.to(points.device),
+                                     focal_y=im.f_y.to(points.device))
+
+    # render_pixel / render_tile (splat/gaussian_scene.py:146-198) are the body of composite_fast_kernel; as public
+    # methods they run that kernel on the caller's depth-ordered list: the op's own entry point (gsb_render_image,
+    # REF_CPU semantics: one sigmoid on `opacities` inside, exactly like :164) on a canvas that reaches the region,
+    # every row's bounding box set to the region so that it is a candidate for all of its pixels.
+    def _render_region(self, x0: int, y0: int, w: int, h: int, means, colors, opacities, inverse_covariance,
+                       min_weight: float) -> torch.Tensor:
+        if x0 < 0 or y0 < 0:
+            raise RuntimeError("render_tile / render_pixel: pixel coordinates must be non-negative")
+        m = means.shape[0]
+        dev = self.rasterizer.device
+        box = lambda v: torch.full((m,), float(v), device=dev)  # noqa: E731
+        prm = _lib.default_params(full_cover=1, min_weight=float(min_weight))
+        img = self.rasterizer.render_preprocessed(y0 + h, x0 + w, 16, means.to(dev), colors.to(dev),
+                                                  inverse_covariance.to(dev), box(x0), box(x0 + w - 1), box(y0),
+                                                  box(y0 + h - 1), opacities.to(dev), params=prm)
+        return img[y0:y0 + h, x0:x0 + w]  # (h, w, 3), [y][x]
+
+    def render_pixel(self, pixel_coords: torch.Tensor, points_in_tile_mean: torch.Tensor, colors: torch.Tensor,
+                     opacities: torch.Tensor, inverse_covariance: torch.Tensor, min_weight: float = 0.000001) -> torch.Tensor:
+        """Front-to-back blend of a depth-ordered list at one pixel -> (1,1,3) (splat/gaussian_scene.py:146-171)."""
+        px, py = (int(round(float(v))) for v in pixel_coords.reshape(-1)[:2])
+        if float(pixel_coords.reshape(-1)[0]) != px or float(pixel_coords.reshape(-1)[1]) != py:
+            raise RuntimeError("render_pixel: pixel coordinates must be integer-valued (the reference passes integer pixels)")
+        out = self._render_region(px, py, 1, 1, points_in_tile_mean, colors, opacities, inverse_covariance, min_weight)
+        return out.reshape(1, 1, 3).to(points_in_tile_mean.device)
+
+    def render_tile(self, x_min: int, y_min: int, points_in_tile_mean: torch.Tensor, colors: torch.Tensor,
+                    opacities: torch.Tensor, inverse_covariance: torch.Tensor, tile_size: int = 16) -> torch.Tensor:
+        """(tile_size, tile_size, 3) CPU tensor indexed [x % tile_size][y % tile_size] for pixels x_min..x_min+T-1,
+        y_min..y_min+T-1 (splat/gaussian_scene.py:173-198); the list must be in depth order."""
+        T = int(tile_size)
+        reg = self._render_region(int(x_min), int(y_min), T, T, points_in_tile_mean, colors, opacities,
+                                  inverse_covariance, 0.000001).cpu()
+        tile = torch.zeros((T, T, 3))
+        xs = (torch.arange(int(x_min), int(x_min) + T) % T)
+        ys = (torch.arange(int(y_min), int(y_min) + T) % T)
+        tile[xs[:, None], ys[None, :]] = reg.transpose(0, 1)  # reg is [y][x]
+        return tile
 
     def preprocess(self, image_idx: int) -> PreprocessedScene:
         rast = self._sync_gaussians()

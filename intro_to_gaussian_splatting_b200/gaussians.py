@@ -34,6 +34,26 @@ class Gaussians(nn.Module):
         self.quaternions[:, 0] = 1.0
         self.opacity = inverse_sigmoid(0.9999 * torch.ones((self.points.shape[0], 1), dtype=torch.float)).to(self.device)
 
+    @classmethod
+    def from_ply(cls, path: str, model_path: str = ".") -> "Gaussians":
+        """A complete Gaussian set from a PLY: this package's native record or the 3DGS trainers' layout
+        (ply_io.load_gaussians).  What the reference cannot do: its loader restores positions and colours only
+        (splat/utils.py:93-99) and the constructor hard-codes the rest (splat/gaussians.py:23-33)."""
+        from .ply_io import load_gaussians
+
+        a = load_gaussians(path)
+        g = cls(points=torch.from_numpy(a["points"]), colors=torch.from_numpy(a["colors"]) * 256, model_path=model_path)
+        g.scales = torch.from_numpy(a["scales"]).to(g.device).float()
+        g.quaternions = torch.from_numpy(a["quaternions"]).to(g.device).float()
+        g.opacity = torch.from_numpy(a["opacity"]).to(g.device).float()
+        return g
+
+    def save_ply(self, path: str, layout: str = "native") -> None:
+        """Persist all five attribute tensors (ply_io.save_gaussians)."""
+        from .ply_io import save_gaussians
+
+        save_gaussians(path, self.points, self.scales, self.quaternions, self.colors, self.opacity, layout=layout)
+
     def get_3d_covariance_matrix(self) -> torch.Tensor:
         """R S S^T R^T per Gaussian (splat/gaussians.py:54-69).  Kept for API parity; the render
         path computes this inside csrc/project.cu and never calls it."""

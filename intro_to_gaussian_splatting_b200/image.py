@@ -7,11 +7,12 @@ import torch
 
 from ._lib import GsbCamera
 from .colmap_io import Camera, Image
-from .utils import build_rotation, focal2fov, getProjectionMatrix, getWorld2View
+from .utils import (build_rotation, focal2fov, get_extrinsic_matrix, get_intrinsic_matrix, getProjectionMatrix, getWorld2View,
+                    in_view_frustum, ndc2Pix)
 
 
 class GaussianImage(torch.nn.Module):
-    """Same attributes as the reference class (1-element / 4x4 fp32 tensors on `self.device`).
+    """Same attributes and method as the reference class (1-element / 3x4 / 4x4 fp32 tensors on `self.device`).
 
     Only PINHOLE-style params[0..3] = fx, fy, cx, cy are read, as in splat/image.py:28-31."""
 
@@ -54,7 +55,23 @@ class GaussianImage(torch.nn.Module):
         self.projection_matrix = projection_matrix.contiguous().to(dev)
         self.full_proj_transform = full_proj_transform.contiguous().to(dev)
         self.camera_center = camera_center.to(dev)
+        # pinhole matrices the render path never reads; kept because callers of the reference class can (splat/image.py:32-40,:68-70)
+        self.intrinsic_matrix = get_intrinsic_matrix(f_x=f_x, f_y=f_y, c_x=c_x, c_y=c_y).to(dev)
+        self.extrinsic_matrix = get_extrinsic_matrix(R[0], T).to(dev)
+        self.projection = (self.intrinsic_matrix.cpu() @ self.extrinsic_matrix.cpu()).to(dev)
         self._packed = None
+
+    def project_point_to_camera_perspective_projection(self, points: torch.Tensor, colors: torch.Tensor):
+        """In-view points -> (pixel x, pixel y, NDC z) and their colours, in Gaussian-index order: the debug scatter of
+        splat/image.py:72-90 (clip = [p 1] @ full_proj_transform; xyz / w; ndc2Pix on x and y)."""
+        keep = in_view_frustum(points=points, view_matrix=self.world2view.to(points.device))
+        pts = points[keep]
+        hom = torch.cat([pts, torch.ones((pts.shape[0], 1), device=pts.device, dtype=pts.dtype)], dim=1)
+        clip = hom @ self.full_proj_transform.to(pts.device)
+        out = clip[:, :3] / clip[:, 3].unsqueeze(1)
+        out[:, 0] = ndc2Pix(out[:, 0], self.width.to(pts.device))
+        out[:, 1] = ndc2Pix(out[:, 1], self.height.to(pts.device))
+        return out, colors[keep]
 
     def pack(self) -> GsbCamera:
         """The GsbCamera struct that crosses the C ABI: the tensors above, bit for bit."""

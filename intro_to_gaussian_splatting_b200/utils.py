@@ -78,3 +78,46 @@ def getProjectionMatrix(znear: torch.Tensor, zfar: torch.Tensor, fovX: torch.Ten
 def ndc2Pix(points: torch.Tensor, dimension) -> torch.Tensor:
     """(v + 1) * (S - 1) * 0.5 (splat/utils.py:313-317)."""
     return (points + 1) * (dimension - 1) * 0.5
+
+
+# ---- The functions below are the per-Gaussian conventions of splat/utils.py that the frozen scene API still
+# exposes through public methods (GaussianImage.project_point_to_camera_perspective_projection,
+# GaussianScene.get_2d_covariance).  They are torch restatements for callers of those methods -- debugging helpers in
+# the reference too (splat/gaussian_scene.py:44-51) -- and deliberately keep the reference's operator order, because
+# that order IS the contract (SURVEY.md Appendix A).  The render path does not call them: csrc/project.cu does this
+# arithmetic for every frame.
+def get_intrinsic_matrix(f_x, f_y, c_x, c_y) -> torch.Tensor:
+    """3x4 pinhole matrix [[fx 0 cx 0] [0 fy cy 0] [0 0 1 0]] (splat/utils.py:19-37)."""
+    k = torch.zeros((3, 4))
+    k[0, 0], k[0, 2], k[1, 1], k[1, 2], k[2, 2] = float(f_x), float(c_x), float(f_y), float(c_y), 1.0
+    return k
+
+
+def get_extrinsic_matrix(R: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """4x4 [[R t] [0 1]] (splat/utils.py:40-52)."""
+    return getWorld2View(R, t)
+
+
+def in_view_frustum(points: torch.Tensor, view_matrix: torch.Tensor, minimum_z: float = 0.2) -> torch.Tensor:
+    """z of [p 1] @ view_matrix >= minimum_z: the only cull of the reference (splat/utils.py:293-310)."""
+    hom = torch.cat([points, torch.ones((points.shape[0], 1), device=points.device, dtype=points.dtype)], dim=1)
+    return (hom @ view_matrix)[:, 2] >= minimum_z
+
+
+def compute_2d_covariance(points: torch.Tensor, extrinsic_matrix: torch.Tensor, covariance_3d: torch.Tensor,
+                          tan_fovY: torch.Tensor, tan_fovX: torch.Tensor, focal_x: torch.Tensor,
+                          focal_y: torch.Tensor) -> torch.Tensor:
+    """EWA projection J W Sigma W^T J^T [:2,:2] with x/z, y/z clamped to +-1.3 tan(fov/2) and NO low-pass term
+    (splat/utils.py:320-354; argument order as there: tan_fovY before tan_fovX)."""
+    hom = torch.cat([points, torch.ones((points.shape[0], 1), device=points.device, dtype=points.dtype)], dim=1)
+    v = (hom @ extrinsic_matrix)[:, :3]
+    z = v[:, 2]
+    x = torch.clamp(v[:, 0] / z, -1.3 * tan_fovX, 1.3 * tan_fovX) * z
+    y = torch.clamp(v[:, 1] / z, -1.3 * tan_fovY, 1.3 * tan_fovY) * z
+    J = torch.zeros((v.shape[0], 3, 3), device=covariance_3d.device)
+    J[:, 0, 0] = focal_x / z
+    J[:, 0, 2] = -(focal_x * x) / (z**2)
+    J[:, 1, 1] = focal_y / z
+    J[:, 1, 2] = -(focal_y * y) / (z**2)
+    W = extrinsic_matrix[:3, :3].T
+    return (J @ W @ covariance_3d @ W.T @ J.transpose(1, 2))[:, :2, :2]

@@ -31,7 +31,7 @@ def test_header_and_library_agree():
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.GsbCamera) == 16 * 4 * 2 + 4 * 4 + 2 * 4
     assert C.sizeof(_lib.GsbParams) == 15 * 4
-    assert C.sizeof(_lib.GsbFrameInfo) == 3 * 8 + 6 * 4 + 2 * 8 + 2 * 4
+    assert C.sizeof(_lib.GsbFrameInfo) == 3 * 8 + 6 * 4 + 2 * 8 + 2 * 4 + 8 + 2 * 4
 
 
 def test_struct_layouts_match_a_c_compiler(tmp_path):

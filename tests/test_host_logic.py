@@ -5,6 +5,7 @@ import struct
 import tempfile
 
 import numpy as np
+import pytest
 import torch
 
 from intro_to_gaussian_splatting_b200 import Gaussians
@@ -65,6 +66,51 @@ def test_ply_round_trip_and_constructor_side_effect():
     assert abs(float(g.opacity[0]) - float(np.log(0.9999 / (1 - 0.9999)))) < 1e-2
     c3 = g.get_3d_covariance_matrix()
     assert c3.shape == (300, 3, 3) and torch.allclose(c3[0].cpu(), torch.eye(3) * 1e-6, atol=1e-9)
+
+
+def test_full_record_ply_round_trips_in_both_layouts():
+    """scales / rotations / opacity persist (the reference's PLY only holds xyz + rgb)."""
+    from intro_to_gaussian_splatting_b200.ply_io import load_gaussians, save_gaussians
+
+    sc = make_scene("small")
+    d = tempfile.mkdtemp()
+    cols = (sc.rgb255 / 256).float()
+    arrs = dict(points=sc.xyz, scales=sc.scales, quaternions=sc.quats, colors=cols, opacity=sc.opacity_logit)
+    # native: bit-exact
+    p1 = os.path.join(d, "native.ply")
+    save_gaussians(p1, *arrs.values())
+    got = load_gaussians(p1)
+    for k, t in arrs.items():
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], t.numpy().reshape(got[k].shape)), k
+    # 3DGS property names: log scales and f_dc colours round-trip to float rounding
+    p2 = os.path.join(d, "point_cloud.ply")
+    save_gaussians(p2, *arrs.values(), layout="3dgs")
+    raw = open(p2, "rb").read(600).decode("ascii", "replace")
+    for prop in ("f_dc_0", "scale_2", "rot_3", "opacity"):
+        assert f"property float {prop}" in raw
+    got = load_gaussians(p2)
+    assert np.array_equal(got["points"], sc.xyz.numpy()) and np.array_equal(got["quaternions"], sc.quats.numpy())
+    assert np.array_equal(got["opacity"], sc.opacity_logit.numpy())
+    assert np.allclose(got["scales"], sc.scales.numpy(), rtol=2e-6) and np.allclose(got["colors"], cols.numpy(), atol=2e-7)
+    # a trained 3DGS file also carries higher SH degrees and normals: extra properties are ignored
+    from intro_to_gaussian_splatting_b200.ply_io import _read_vertices, _write
+    v, _ = _read_vertices(p2)
+    wide = np.zeros(v.shape[0], dtype=np.dtype(v.dtype.descr + [(f"f_rest_{i}", "<f4") for i in range(45)]))
+    for k in v.dtype.names:
+        wide[k] = v[k]
+    _write(p2, wide)
+    assert np.array_equal(load_gaussians(p2)["points"], sc.xyz.numpy())
+    # the container: from_ply / save_ply
+    g = Gaussians.from_ply(p1, model_path=d)
+    assert torch.equal(g.scales.cpu(), sc.scales) and torch.equal(g.quaternions.cpu(), sc.quats)
+    assert torch.equal(g.opacity.cpu(), sc.opacity_logit) and torch.allclose(g.colors.cpu(), cols, atol=1e-7)
+    g.save_ply(os.path.join(d, "again.ply"))
+    assert np.array_equal(load_gaussians(os.path.join(d, "again.ply"))["scales"], sc.scales.numpy())
+    storePly(os.path.join(d, "xyz_rgb_only.ply"), sc.xyz.numpy(), sc.rgb255.numpy())
+    with pytest.raises(ValueError):  # the reference's own layout has no scales / rotations / opacity to load
+        load_gaussians(os.path.join(d, "xyz_rgb_only.ply"))
+    with pytest.raises(ValueError):
+        save_gaussians(p1, sc.xyz, sc.scales[:-1], sc.quats, cols, sc.opacity_logit)
 
 
 def test_synth_is_deterministic_and_matches_its_spec():
