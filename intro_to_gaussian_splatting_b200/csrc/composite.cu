@@ -184,6 +184,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// -DGSB_STAGE_BULK: stage the records with cp.async.bulk (the TMA unit's 1-D bulk copy, one 48-byte copy per record,
+// completion counted in bytes on an mbarrier per buffer) instead of three LDGSTS per record.  Built on request only
+// (tools/build_variant.sh bulk -DGSB_STAGE_BULK): measured on B200, profiles/r2_summary.md.
+#ifdef GSB_STAGE_BULK
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+  unsigned ok = 0;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_copy48(void* smem_dst, const void* gmem_src, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 48, [%2];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+#endif
+
 // max over t in [lo, hi] of  q t^2 + s t + c0  for q < 0;  rq = 1 / (2 q)
 __device__ __forceinline__ float edge_max(float q, float s, float lo, float hi, float rq, float c0) {
   const float t = fminf(fmaxf(-s * rq, lo), hi);
@@ -248,6 +271,9 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
                                                                     // records that survive culling
   __shared__ uint32_t s_cnt[2][4];                                  // filter round: hits per (warp, entry half)
   __shared__ uint32_t s_dead[2];                                    // warp w has no live pixel left
+#ifdef GSB_STAGE_BULK
+  __shared__ __align__(8) uint64_t s_mbar[2];                       // one per record buffer, every thread arrives
+#endif
   if (abort && *abort) return;  // the lists do not exist: the host re-queues the frame's tail (gsb_api.cu)
 
   const int tile = blockIdx.x;
@@ -286,6 +312,10 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
     float4* d = &sm[tid][kFastBatch * 3];
     d[0] = make_float4(0.f, 0.f, 0.f, 0.f); d[1] = make_float4(0.f, 0.f, -INFINITY, 0.f); d[2] = d[0];
     s_dead[tid] = 0u;
+#ifdef GSB_STAGE_BULK
+    mbar_init(&s_mbar[tid], kFastThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   }
 
   bool l0 = px < a.width && py0 < a.height, l1 = px < a.width && py0 + 1 < a.height;
@@ -328,6 +358,13 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
   };
   // stage the ring's next `cnt` indices as records of buffer `buf`; list_pos = position of the batch in the tile's list
   auto stage = [&](int buf, uint32_t cnt, uint32_t list_pos) {
+#ifdef GSB_STAGE_BULK
+    unsigned mine = 0;
+#pragma unroll
+    for (int j = 0; j < kFastPerThread; ++j)
+      if ((uint32_t)(j * kFastThreads + tid) < cnt) mine += 48u;
+    mbar_arrive_expect_tx(&s_mbar[buf], mine);  // every thread arrives once per use of the buffer
+#endif
 #pragma unroll
     for (int j = 0; j < kFastPerThread; ++j) {
       const uint32_t r = (uint32_t)(j * kFastThreads + tid);
@@ -335,11 +372,17 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
         const uint32_t g = s_ring[(head + r) & (kRing - 1)];
         const float4* s3 = rec + 3 * (size_t)g;
         float4* dst = &sm[buf][r * 3];
+#ifdef GSB_STAGE_BULK
+        bulk_copy48(dst, s3, &s_mbar[buf]);
+#else
         cp_async16(dst, s3); cp_async16(dst + 1, s3 + 1); cp_async16(dst + 2, s3 + 2);
+#endif
         if (kAux && kMasked) out_list[list_pos + r] = g;
       }
     }
+#ifndef GSB_STAGE_BULK
     cp_async_commit();
+#endif
   };
   // survivor masks of the batch resident in buffer `buf`: record slot j*64 + tid is bit `lane` of word 2j + warp
   auto build_masks = [&](int buf, uint32_t cnt) {
@@ -368,7 +411,11 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
   bool warp_live = true;
   for (uint32_t b = 0; cnt_cur > 0u; ++b) {
     const int buf = (int)(b & 1u);
+#ifdef GSB_STAGE_BULK
+    mbar_wait(&s_mbar[buf], (b >> 1) & 1u);
+#else
     cp_async_wait<0>();
+#endif
     // batch b visible to all; everyone is done with the other buffer and with the ring slots of batch b;
     // stop when no pixel of the tile is live
     if (!__syncthreads_or(warp_live)) break;

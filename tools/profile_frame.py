@@ -21,6 +21,7 @@ ap.add_argument("--sort-mode", default="auto")
 ap.add_argument("--full-cover", type=int, default=1)
 ap.add_argument("--stage-times", type=int, default=0)
 ap.add_argument("--cull-alpha", type=float, default=None)
+ap.add_argument("--checksum", type=int, default=0, help="print a digest of every frame (to compare kernel variants)")
 ap.add_argument("--views", default="", help="comma-separated orbit view numbers to render instead of 0..frames-1")
 a = ap.parse_args()
 views = [int(v) for v in a.views.split(",") if v] or list(range(max(a.frames, 1)))
@@ -43,4 +44,7 @@ for f in views:
     msg = f"frame {f}: M={info.m_in_view} K={info.k_instances} launches={info.kernel_launches}"
     if a.stage_times:
         msg += " " + " ".join(f"{k}={v * 1e3:.1f}us" for k, v in r.stage_times().items())
+    if a.checksum:
+        import hashlib
+        msg += " sha256=" + hashlib.sha256(img.cpu().numpy().tobytes()).hexdigest()[:16]
     print(msg, flush=True)
