@@ -174,7 +174,12 @@ constexpr int kFastThreads = 64;
 constexpr int kFastBatch = 128;                        // records per stage
 constexpr int kFastPerThread = kFastBatch / kFastThreads;  // records each thread stages
 constexpr int kFastUnroll = 4;                         // Gaussians between two warp votes = slots per list word
-constexpr int kRing = 256;                             // survivor ring: < 128 pending + <= 128 from one round
+#ifndef GSB_FILTER_PER
+#define GSB_FILTER_PER 4
+#endif
+constexpr int kFilterPer = GSB_FILTER_PER;             // list entries each thread examines per filter round
+constexpr int kFilterRound = kFilterPer * kFastThreads;  // entries per round
+constexpr int kRing = 512;                             // survivor ring: < 128 pending + <= 256 from one round
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -269,7 +274,7 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
   __shared__ uint32_t s_ring[kRing];                                // Gaussian indices of the tile's list, in order
   __shared__ __align__(8) uint16_t s_list[2][kFastBatch + 8];       // per warp: shared-memory addresses (16 bits) of the
                                                                     // records that survive culling
-  __shared__ uint32_t s_cnt[2][4];                                  // filter round: hits per (warp, entry half)
+  __shared__ uint32_t s_cnt[2][2 * kFilterPer];                     // filter round: hits per (entry slice, warp)
   __shared__ uint32_t s_dead[2];                                    // warp w has no live pixel left
 #ifdef GSB_STAGE_BULK
   __shared__ __align__(8) uint64_t s_mbar[2];                       // one per record buffer, every thread arrives
@@ -328,10 +333,10 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
 
   // ---- list filter: entries pos .. pos+127 per round, hits appended to the ring ----
   uint32_t pos = 0, head = 0, tail = 0;  // entries examined; ring indices consumed / produced (uniform over the CTA)
-  uint32_t e_g[kFastPerThread], e_hit[kFastPerThread];
-  auto prefetch = [&]() {  // this thread's entries of the next round: pos + tid and pos + 64 + tid
+  uint32_t e_g[kFilterPer], e_hit[kFilterPer];
+  auto prefetch = [&]() {  // this thread's entries of the next round: pos + 64 j + tid
 #pragma unroll
-    for (int j = 0; j < kFastPerThread; ++j) {
+    for (int j = 0; j < kFilterPer; ++j) {
       const uint32_t i = pos + j * kFastThreads + tid;
       e_g[j] = 0u; e_hit[j] = 0u;
       if (i < len) {
@@ -343,15 +348,22 @@ composite_fast_kernel(const __grid_constant__ TileSource src, const float4* __re
   int parity = 0;
   auto fill = [&]() {  // until a full batch is pending or the list is exhausted
     while (tail - head < (uint32_t)kFastBatch && pos < len) {
-      const unsigned h0 = __ballot_sync(0xffffffffu, e_hit[0] != 0u), h1 = __ballot_sync(0xffffffffu, e_hit[1] != 0u);
-      if (lane == 0) { s_cnt[parity][2 * warp] = (uint32_t)__popc(h0); s_cnt[parity][2 * warp + 1] = (uint32_t)__popc(h1); }
+      unsigned h[kFilterPer];
+#pragma unroll
+      for (int j = 0; j < kFilterPer; ++j) {
+        h[j] = __ballot_sync(0xffffffffu, e_hit[j] != 0u);
+        if (lane == 0) s_cnt[parity][2 * j + warp] = (uint32_t)__popc(h[j]);  // list order: slice j, then warp
+      }
       __syncthreads();
-      // list order of the round: (warp 0, first half) (warp 1, first half) (warp 0, second half) (warp 1, second half)
-      const uint32_t c00 = s_cnt[parity][0], c01 = s_cnt[parity][1], c10 = s_cnt[parity][2], c11 = s_cnt[parity][3];
-      if (e_hit[0]) s_ring[(tail + (warp ? c00 : 0u) + (uint32_t)__popc(h0 & lt_mask)) & (kRing - 1)] = e_g[0];
-      if (e_hit[1]) s_ring[(tail + c00 + c10 + (warp ? c01 : 0u) + (uint32_t)__popc(h1 & lt_mask)) & (kRing - 1)] = e_g[1];
-      tail += c00 + c01 + c10 + c11;
-      pos += (uint32_t)kFastBatch;
+      uint32_t o = tail;
+#pragma unroll
+      for (int j = 0; j < kFilterPer; ++j) {
+        const uint32_t c0 = s_cnt[parity][2 * j], c1 = s_cnt[parity][2 * j + 1];
+        if (e_hit[j]) s_ring[(o + (warp ? c0 : 0u) + (uint32_t)__popc(h[j] & lt_mask)) & (kRing - 1)] = e_g[j];
+        o += c0 + c1;
+      }
+      tail = o;
+      pos += (uint32_t)kFilterRound;
       parity ^= 1;
       prefetch();
     }
