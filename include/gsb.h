@@ -152,7 +152,9 @@ int gsb_upload(GsbContext* ctx, int64_t n, const float* xyz, const float* scales
  * the frame's counts fit, and the call returns once those counts (M, K) have reached the host through a
  * mailbox in mapped pinned memory -- the stream is never drained and never waits for the host.  Only when
  * a count outgrew its buffer (first frames, or a view with many more tile instances) does the host grow
- * the buffer and queue the tail of the frame again. */
+ * the buffer and queue the tail of the frame again.  `stream` must be able to make progress without further
+ * action of the calling thread (no wait on an event that is only recorded later): the call waits, on the host, for
+ * the frame's projection to have run, and gives up with GSB_E_INTERNAL after two minutes. */
 int gsb_render(GsbContext* ctx, const GsbCamera* cam, const GsbParams* params, float* out_image,
                void* stream);
 
