@@ -10,15 +10,14 @@
 //     C += T * alpha * c;  T = test
 // No per-pixel bbox test, no alpha clamp, no 1/255 skip.
 //
-// One CTA per 16x16 tile, one thread per pixel; each warp owns an 8x4 pixel block so that early
-// termination is spatially coherent.  The tile's instance list is staged through shared memory in
-// batches of 256: thread t gathers the 48-byte record of instance batch+t (prefetched into registers
-// one batch ahead, so the gather latency hides behind the blend loop), every thread then reads the
-// records as shared-memory broadcasts.  A warp leaves the blend loop when all its pixels are done; the
-// CTA stops fetching batches when __syncthreads_and says every pixel is done.
+// Two kernels:
+//   composite_fast_kernel   REF_CPU, the frame path: 64 threads per tile, four pixels per thread, list filtered from
+//                           the super-tile's list on the fly, per-warp culling (documented at the kernel)
+//   composite_kernel<REF_CU> render.cu's arithmetic over materialised per-tile lists: one thread per pixel, 8x4 pixels
+//                           per warp, batches of 256 records gathered through registers into shared memory
 //
-// Roofline: issue slots (fp32 FMA/ALU + MUFU.EX2), not HBM: ~20 warp-instructions per
-// (warp, Gaussian) step; HBM traffic is 4 B payload + 48 B record per instance + 12 B per pixel.
+// Roofline: issue slots (fp32 FMA/ALU + MUFU.EX2 out of shared memory), not HBM: 16.4 SASS instructions per
+// executed (pixel, Gaussian) step in the fast kernel; DRAM traffic 22 MB per 1080p frame (the records are L2 resident).
 #include <cmath>
 #include <cstdlib>
 
@@ -143,7 +142,7 @@ composite_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 //
 // Where the tile's list comes from (kMasked).  SPLIT mode never stores per-tile lists: the tile reads the list of
 // its SUPER-TILE (8 x 4 tiles; entries {Gaussian index, 32-bit tile mask} in depth order, written by the last radix
-// pass) and keeps the entries whose mask has the tile's bit -- 128 entries per round, two ballots per warp, the
+// pass) and keeps the entries whose mask has the tile's bit -- 256 entries per round, four ballots per warp, the
 // survivors' indices go into a small ring in shared memory.  Early termination therefore also ends the binning
 // work: a tile that saturates after 350 Gaussians never looks at the rest of its super-tile's list, where a
 // separate expansion pass would have written (and this kernel read back) all of it.  FULL mode and one-level SPLIT
