@@ -590,7 +590,7 @@ def run_ours(args):
                     "traffic": cal_stage["composite"]["dram_bytes"],
                     "launch_ms": round(comp_ms0, 4),
                     "warp_inst_per_launch": int(winst),
-                    "warp_inst_per_pixel_step": (round(winst / calib["oracle_steps"], 4) if calib.get("oracle_steps") else None),
+                    "warp_inst_per_pixel_step": None,  # filled in below when the cpu_baseline leg counted the steps
                     "peak_source": f"{n_sm} SMs x 4 schedulers x SM clock sampled during the run ({sm_mhz:.0f} MHz)",
                     "calibration": {"file": os.path.relpath(CALIBRATION, ROOT), "view": 0,
                                     "note": "warp instructions and DRAM bytes of this kernel for orbit view 0, from an ncu "
@@ -602,8 +602,12 @@ def run_ours(args):
                     "traffic": (cal_stage.get(dom["stage"], {}) or {}).get("dram_bytes"),
                     "launch_ms": dom["ms"], "peak_source": peak_src}
         if dom["stage"] == "composite":
-            roofline["note"] = ("compositing is issue-slot bound; no ncu calibration for this config / build, so only the "
-                                "(upper-bound) HBM figure is reported")
+            # 52 B per (tile, Gaussian) instance is an UPPER bound of what the kernel reads (early termination, records
+            # served from L2): it is not a fraction of anything
+            roofline.update({"bound": "issue", "achieved": None, "peak": None, "unit": "Gwarp-inst/s", "frac": None,
+                             "hbm_upper_bound_gbs": dom["achieved_gbs"],
+                             "note": "compositing is issue-slot bound; no ncu calibration for this config / build "
+                                     "(tools/calibrate_roofline.py --config ...), so no fraction is reported"})
     roofline["stages"] = stages
     roofline["hbm_peak_gbs"] = hbm_peak
     roofline["hbm_peak_source"] = peak_src
@@ -685,6 +689,7 @@ def run_ours(args):
                                     "steps_executed_view0": int(fr.steps)}
             if roofline.get("bound") == "issue":
                 roofline["pixel_steps_view0_this_run"] = int(fr.steps)
+                roofline["warp_inst_per_pixel_step"] = round(roofline["warp_inst_per_launch"] / int(fr.steps), 4)
         except Exception as e:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)

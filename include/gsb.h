@@ -41,7 +41,8 @@ extern "C" {
 #define GSB_E_INVALID_ARG (-1)
 #define GSB_E_NO_SCENE (-2)      /* render before gsb_upload */
 #define GSB_E_NO_FRAME (-3)      /* debug getter before a render */
-#define GSB_E_UNSUPPORTED (-4)   /* e.g. tile_size != 16, image too large for the key layout */
+#define GSB_E_UNSUPPORTED (-4)   /* e.g. tile_size != 16, image too large for the key layout, or a render call on a
+                                    stream the caller is capturing (the host needs the frame's counts) */
 #define GSB_E_NO_DEVICE (-5)     /* no usable CUDA device: the library has NO CPU fallback */
 #define GSB_E_ALLOC (-6)
 #define GSB_E_INTERNAL (-7)   /* a device-side consistency check failed */
@@ -124,7 +125,7 @@ typedef struct GsbFrameInfo {
   int32_t super_w, super_h; /* SPLIT: tiles per super-tile (1 x 1: single-level binning) */
   int64_t v_with_tiles; /* in-view Gaussians whose tile rect is not empty (the rows the binning stages touch) */
   int32_t tail_requeued; /* 1: a count outgrew the capacities the frame was queued with and its tail was queued twice */
-  int32_t reserved;
+  int32_t graph_launch;     /* 1: the frame went out as ONE CUDA graph launch (non-default stream, no stage timing) */
 } GsbFrameInfo;
 
 typedef struct GsbContext GsbContext;

@@ -82,7 +82,7 @@ class GsbFrameInfo(C.Structure):
         ("super_h", C.c_int32),
         ("v_with_tiles", C.c_int64),
         ("tail_requeued", C.c_int32),
-        ("reserved", C.c_int32),
+        ("graph_launch", C.c_int32),
     ]
 
 

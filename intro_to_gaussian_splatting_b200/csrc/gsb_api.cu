@@ -144,6 +144,10 @@ struct GsbContext {
   uint32_t* pinned = nullptr;      // mailbox written by tile_stats_kernel: {M, V, K lo, K hi, seq, abort, Ks lo, Ks hi}
   uint32_t* pinned_dev = nullptr;  // device alias of the mailbox
   uint32_t seq = 0;
+  // the frame as ONE CUDA graph (see FrameCapture): instantiated once, updated in place every frame
+  bool allow_graph = true;
+  cudaGraphExec_t frame_exec = nullptr;
+  bool stats_in_graph = false;  // this frame's tile_stats launches run inside the graph on the caller's stream
   cudaStream_t aux = nullptr;   // side stream for work that is off the critical path (tile stats)
   cudaEvent_t ev_fork = nullptr, ev_stats = nullptr;
   // asynchronous image egress: two device staging images, a copy stream, one event per staging image
@@ -191,6 +195,73 @@ struct StageTimer {
   }
 };
 
+// The frame as one CUDA graph.  A frame is 11 kernels + 2 memsets + an event fork / join, all queued before the host
+// reads anything (section "queue first" of DESIGN.md): captured from the very same launch code (relaxed stream
+// capture, the auxiliary stream joins the capture through its events), then cudaGraphExecUpdate writes this frame's
+// kernel arguments (camera, mailbox sequence number, image pointer, buffer addresses) into the graph instantiated by
+// the first frame, and ONE cudaGraphLaunch submits it.  Why: each stream command is fetched by the GPU from host
+// memory, and while image copies saturate PCIe every such fetch waits ~35 us behind them (measured,
+// tools/e2e_probe.py) -- eleven of them per frame cost the end-to-end figure 14 %.  Not used on the legacy default
+// stream (capture is not allowed there), inside a caller's own capture, or with stage timing on.
+struct FrameCapture {
+  GsbContext* c;
+  cudaStream_t st;
+  bool active = false;
+  int begin() {
+    GSB_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    active = true;
+    c->stats_in_graph = true;
+    return GSB_OK;
+  }
+  // end of the queued frame: instantiate / update, launch.  No-op when nothing is being captured.
+  int submit() {
+    if (!active) return GSB_OK;
+    active = false;
+    cudaGraph_t g = nullptr;
+    GSB_CUDA_TRY(cudaStreamEndCapture(st, &g));
+    if (c->frame_exec) {
+      cudaGraphExecUpdateResultInfo why;
+      if (cudaGraphExecUpdate(c->frame_exec, g, &why) != cudaSuccess) {  // another topology (pass count, key width, ...)
+        cudaGetLastError();
+        cudaGraphExecDestroy(c->frame_exec);
+        c->frame_exec = nullptr;
+      }
+    }
+    cudaError_t e = cudaSuccess;
+    if (!c->frame_exec) e = cudaGraphInstantiate(&c->frame_exec, g, 0);
+    cudaGraphDestroy(g);
+    GSB_CUDA_TRY(e);
+    GSB_CUDA_TRY(cudaGraphLaunch(c->frame_exec, st));
+    c->info.graph_launch = 1;
+    return GSB_OK;
+  }
+  ~FrameCapture() {  // an error path left the stream capturing: drop what was captured, nothing of it ran
+    if (!active) return;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    c->stats_in_graph = false;
+  }
+};
+
+// A caller's own capture cannot contain a frame: the host waits for the frame's counts, which a captured frame never
+// produces.  Refuse instead of spinning on the mailbox.
+bool caller_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
+// may this frame go out as a graph on `st`?
+bool graph_allowed(GsbContext* c, cudaStream_t st, const GsbParams* prm) {
+  if (!c->allow_graph || prm->collect_stage_times) return false;
+  if (st == nullptr || st == cudaStreamLegacy) return false;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs == cudaStreamCaptureStatusNone;
+}
+
 int check_params(const GsbCamera* cam, const GsbParams* prm) {
   if (!cam || !prm) return GSB_E_INVALID_ARG;
   if (prm->tile_size != kTile) return GSB_E_UNSUPPORTED;
@@ -209,6 +280,7 @@ void begin_frame(GsbContext* c) {
   c->have_order = false;
   c->have_saved = false;
   c->have_times = false;
+  c->stats_in_graph = false;
   ++c->frame_id;
   std::memset(&c->info, 0, sizeof(c->info));
   c->info.frame_id = c->frame_id;
@@ -262,7 +334,7 @@ int wait_counts(GsbContext* c, int64_t tiles, const uint32_t* ctl, cudaStream_t 
   // acquire: the counts below must not be read before the sequence number (weakly ordered hosts)
   for (uint64_t spins = 0; __atomic_load_n(&box[4], __ATOMIC_ACQUIRE) != c->seq; ++spins) {
     if ((spins & 0x3FFF) == 0x3FFF) {
-      cudaError_t q = cudaStreamQuery(c->aux);
+      cudaError_t q = cudaStreamQuery(c->stats_in_graph ? st : c->aux);  // where this frame's tile_stats run
       if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
       if (q == cudaSuccess && __atomic_load_n(&box[4], __ATOMIC_ACQUIRE) != c->seq) return GSB_E_INTERNAL;  // kernel finished, mailbox never written
       // a stream that never runs (e.g. waiting on an event nobody records) must not hang the caller for ever
@@ -492,7 +564,7 @@ TileSource tile_source(GsbContext* c, const SplitPlan* sp) {
 template <typename CompositeFn>
 int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sorted_by_visibility, FrameGeom geom,
               SuperGeom sg, bool payload_side, bool expand_in_stream, uint32_t* ctl, const CtlLayout& L, cudaStream_t st,
-              StageTimer& tm, int* launches, CompositeFn&& queue_composite) {
+              StageTimer& tm, int* launches, FrameCapture* cap, CompositeFn&& queue_composite) {
   const int64_t tiles = (int64_t)geom.tiles_x * geom.tiles_y;
   if (tiles <= 0 || n_rows <= 0) {  // nothing to bin; the compositing launcher handles an empty grid itself
     Counts cn;
@@ -521,6 +593,7 @@ int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sor
   read_capacities(c, sp);  // the capacities tile_stats_kernel was given (launch_stats_async ran with the same values)
   GSB_TRY(queue_split_tail(c, n_rows, perm, v_limit, geom, sp, ctl, L, st, tm, launches));
   GSB_TRY(queue_composite(tile_source(c, &sp), ctl + kCtlAbort));
+  if (cap) GSB_TRY(cap->submit());  // the whole frame is queued: as one graph launch when it was captured
   Counts cn;
   GSB_TRY(wait_counts(c, tiles, ctl, st, &cn));
   if (cn.k >= ((int64_t)1 << 32) - 1 || cn.ks >= ((int64_t)1 << 32) - 1) return GSB_E_UNSUPPORTED;  // positions are u32
@@ -562,6 +635,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   if (!c->planes.p && c->n > 0) return GSB_E_NO_SCENE;
   if (prm->semantics != GSB_SEM_REF_CPU) return GSB_E_UNSUPPORTED;  // REF_CU is served by gsb_render_image
   GSB_CUDA_TRY(cudaSetDevice(c->device));
+  if (caller_is_capturing(st)) return GSB_E_UNSUPPORTED;
   const int64_t n = c->n;
   FrameGeom geom{cam->width, cam->height, tile_grid_dim(cam->width, kTile, prm->full_cover),
                  tile_grid_dim(cam->height, kTile, prm->full_cover)};
@@ -585,6 +659,21 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
   uint64_t cap_k = ~0ull, cap_ks = ~0ull;  // FULL: the host sizes everything after it has seen K
   const bool payload_side = prm->save_for_backward != 0;  // the gradient pass walks per-tile lists as arrays
   if (split && n > 0 && tiles > 0) GSB_TRY(prepare_split(c, n, sg, payload_side, false, &cap_k, &cap_ks));
+  FrameCapture cap{c, st};
+  if (split && n > 0 && tiles > 0 && graph_allowed(c, st, prm)) {
+    // buffers the captured section would otherwise allocate on its way (an allocation is legal in a relaxed
+    // capture, a cudaFree of a grown buffer drains the device: keep both out of it)
+    GSB_TRY(c->ord_keys_a.ensure((size_t)n * 4)); GSB_TRY(c->ord_keys_b.ensure((size_t)n * 4));
+    GSB_TRY(c->ord_vals_a.ensure((size_t)n * 4)); GSB_TRY(c->ord_vals_b.ensure((size_t)n * 4));
+    GSB_TRY(c->offsets.ensure((size_t)n * 4 + 4));
+    GSB_TRY(c->ranges.ensure((size_t)tiles * 8));
+    if (two_level) GSB_TRY(c->ranges_s.ensure((size_t)sg.nx * sg.ny * 8));
+    if (prm->save_for_backward) {
+      GSB_TRY(c->aux_t.ensure((size_t)cam->width * cam->height * 4));
+      GSB_TRY(c->aux_n.ensure((size_t)cam->width * cam->height * 4));
+    }
+    GSB_TRY(cap.begin());
+  }
   GSB_CUDA_TRY(cudaMemsetAsync(c->control.p, 0, L.total * 4, st));
   uint32_t* ctl = c->control.as<uint32_t>();
 
@@ -628,7 +717,7 @@ int render_device(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, flo
       tm.mark(GSB_STAGE_DEPTH_SORT);
     }
     GSB_TRY(run_split(c, n, perm, /*rows_sorted_by_visibility=*/true, geom, sg, payload_side, false, ctl, L, st, tm,
-                      &launches, queue_composite));
+                      &launches, &cap, queue_composite));
   } else {
     if (n > 0 && tiles > 0) {
       GSB_TRY(bin_full(c, n, geom, ctl, L, st, tm, &launches));
@@ -684,7 +773,7 @@ const char* gsb_error_string(int s) {
     case GSB_E_INVALID_ARG: return "invalid argument";
     case GSB_E_NO_SCENE: return "no Gaussians uploaded (call gsb_upload first)";
     case GSB_E_NO_FRAME: return "no frame rendered yet";
-    case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; fewer than 2^32-1 tile instances)";
+    case GSB_E_UNSUPPORTED: return "unsupported configuration (tile_size must be 16; fewer than 2^32-1 tile instances; no render calls inside a caller's stream capture)";
     case GSB_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
     case GSB_E_ALLOC: return "device memory allocation failed";
     case GSB_E_INTERNAL: return "internal error (device-side consistency check failed, or the stream made no progress)";
@@ -729,6 +818,8 @@ int gsb_create(GsbContext** out, int device) {
     set_force_wide_status(e ? std::atoi(e) : 0);
     e = std::getenv("GSB_KEYS32");                        // 0: never use 32-bit keys for the super-tile passes
     c->allow_keys32 = !e || std::atoi(e) != 0;
+    e = std::getenv("GSB_GRAPH");                         // 0: queue every frame launch by launch
+    c->allow_graph = !e || std::atoi(e) != 0;
     e = std::getenv("GSB_SUPER");                         // "lw,lh": log2 tiles per super-tile; "0,0": one level
     if (e) {
       int lw = 3, lh = 2;
@@ -761,6 +852,7 @@ void gsb_destroy(GsbContext* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->frame_exec) cudaGraphExecDestroy(c->frame_exec);
   if (c->aux) cudaStreamDestroy(c->aux);
   if (c->copy) cudaStreamDestroy(c->copy);
   if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
@@ -958,6 +1050,7 @@ int gsb_preprocess(GsbContext* c, const GsbCamera* cam, const GsbParams* prm, in
   if (!c->planes.p && c->n > 0) return GSB_E_NO_SCENE;
   cudaStream_t st = (cudaStream_t)stream;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
+  if (caller_is_capturing(st)) return GSB_E_UNSUPPORTED;
   const int64_t n = c->n;
   begin_frame(c);  // overwrites the per-frame records: a frame saved for the backward pass is gone
   if (m_out) *m_out = 0;
@@ -1026,6 +1119,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
   if (m >= ((int64_t)1 << 31)) return GSB_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   GSB_CUDA_TRY(cudaSetDevice(c->device));
+  if (caller_is_capturing(st)) return GSB_E_UNSUPPORTED;
   const bool cu = prm.semantics == GSB_SEM_REF_CU;
   const int cover = cu ? 1 : prm.full_cover;  // render.cu covers every pixel (:119-124)
   FrameGeom geom{W, H, tile_grid_dim(W, kTile, cover), tile_grid_dim(H, kTile, cover)};
@@ -1091,7 +1185,7 @@ int gsb_render_image(GsbContext* c, int32_t H, int32_t W, int32_t tile_size, int
     return GSB_OK;
   };
   GSB_TRY(run_split(c, m, nullptr, /*rows_sorted_by_visibility=*/false, geom, sg, false, /*expand_in_stream=*/cu, hdr, L, st,
-                    tm, &launches, queue_composite));
+                    tm, &launches, /*cap=*/nullptr, queue_composite));
   c->info.m_in_view = m;
   if (host_out) GSB_CUDA_TRY(cudaMemcpyAsync(out_image, dev_image, bytes, cudaMemcpyDeviceToHost, st));
   c->info.kernel_launches = launches;

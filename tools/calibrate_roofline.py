@@ -5,9 +5,9 @@
 
 Runs `tools/profile_frame.py --views 0,0,0` under ncu (metrics: smsp__inst_executed.sum, dram bytes read/written,
 gpu__time_duration.sum; --clock-control none), keeps the kernels of the LAST frame, groups them into the stages of
-gsb_stage_times, and counts the (pixel, Gaussian) steps of the same view with the oracle.  bench.py divides the
-warp-instruction count of the compositing kernel by its own CUDA-event time of orbit view 0: no constant is typed in
-by hand, and the file says which build it belongs to.  Copy the result to profiles/ after a GPU run.
+gsb_stage_times.  bench.py divides the warp-instruction count of the compositing kernel by its own CUDA-event time of
+orbit view 0 (and, when its cpu_baseline leg ran, by the pixel-steps that leg counted): no constant is typed in by
+hand, and the file says which build it belongs to.  Copy the result to profiles/ after a GPU run.
 """
 import argparse
 import csv
@@ -88,9 +88,10 @@ def main():
         elif m == "gpu__time_duration.sum":
             launches[lid]["us"] = to_us(v, u)
     seq = [launches[i] for i in order if stage_of(launches[i]["name"]) != "other"]
-    # three identical frames: keep the last third
-    per_frame = len(seq) // 3
-    last = seq[-per_frame:]
+    # three identical frames, the first of which may have queued its tail twice (buffers still growing): keep what was
+    # launched from the last projection on
+    first = max(i for i, k in enumerate(seq) if stage_of(k["name"]) == "project")
+    last = seq[first:]
     stages = {}
     for k in last:
         s = stages.setdefault(stage_of(k["name"]), {"warp_inst": 0.0, "dram_bytes": 0.0, "ncu_us": 0.0, "launches": 0})
@@ -98,25 +99,6 @@ def main():
         s["dram_bytes"] += k.get("dram_bytes", 0.0)
         s["ncu_us"] += k.get("us", 0.0)
         s["launches"] += 1
-
-    # executed (pixel, Gaussian) steps of the same view under reference semantics: the oracle counts them
-    import ctypes as C
-
-    from intro_to_gaussian_splatting_b200.colmap_io import read_camera_file, read_image_file
-    from intro_to_gaussian_splatting_b200.image import GaussianImage
-    from intro_to_gaussian_splatting_b200.synth import CONFIGS, make_scene, write_colmap_text
-    from oracle import oracle as orc
-
-    sc = make_scene(CONFIGS[a.config], n_views=1)
-    d = tempfile.mkdtemp()
-    write_colmap_text(sc, d)
-    cams, imgs = read_camera_file(d), read_image_file(d)
-    cam = GaussianImage(cams[imgs[1].camera_id], imgs[1]).pack()
-    ocam = orc.Camera()
-    C.memmove(C.byref(ocam), C.byref(cam), C.sizeof(cam))
-    orc.set_num_threads(len(os.sched_getaffinity(0)))
-    fr = orc.render(ocam, orc.default_params(full_cover=a.full_cover), sc.xyz.numpy(), sc.scales.numpy(), sc.quats.numpy(),
-                    (sc.rgb255 / 256).float().numpy(), sc.opacity_logit.numpy())
 
     try:
         rev = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
@@ -134,19 +116,17 @@ def main():
         except Exception:
             out = {}
     out.setdefault("frames", {})[key] = {
-        "view": 0, "oracle_steps": int(fr.steps), "k_instances": int(fr.keys.shape[0]), "stages": stages,
+        "view": 0, "stages": stages,
         "kernels": [{"name": k["name"][:120], "warp_inst": k.get("warp_inst"), "dram_bytes": k.get("dram_bytes"), "us": k.get("us")}
                     for k in last],
     }
-    out["how"] = ("ncu --metrics " + METRICS + " --clock-control none over tools/profile_frame.py --views 0,0,0 (last frame kept); "
-                  "oracle_steps = (pixel, Gaussian) steps the reference semantics execute for that view (oracle/gs_oracle.c)")
+    out["how"] = ("ncu --metrics " + METRICS + " --clock-control none over tools/profile_frame.py --views 0,0,0 (last frame kept)")
     out["build"] = {"git": rev, "lib_sha256_16": lib_sha}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
     c = stages.get("composite", {})
     print(f"{key}: composite {c.get('warp_inst', 0) / 1e6:.1f} M warp inst, {c.get('dram_bytes', 0) / 1e6:.1f} MB DRAM, "
-          f"{c.get('ncu_us', 0):.1f} us under ncu; {fr.steps / 1e6:.1f} M pixel-steps -> "
-          f"{c.get('warp_inst', 0) / max(fr.steps, 1):.4f} warp inst / step")
+          f"{c.get('ncu_us', 0):.1f} us under ncu")
 
 
 if __name__ == "__main__":
