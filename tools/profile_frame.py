@@ -41,7 +41,8 @@ for f in views:
     r.render(packed[f], prm, out=img)
     torch.cuda.synchronize()
     info = r.frame_info()
-    msg = f"frame {f}: M={info.m_in_view} K={info.k_instances} launches={info.kernel_launches}"
+    msg = (f"frame {f}: M={info.m_in_view} V={info.v_with_tiles} K={info.k_instances} Ks={info.k_sorted} "
+           f"key_bits={info.key_bits} launches={info.kernel_launches}")
     if a.stage_times:
         msg += " " + " ".join(f"{k}={v * 1e3:.1f}us" for k, v in r.stage_times().items())
     if a.checksum:
