@@ -622,6 +622,9 @@ def run_ours(args):
         "config": {"workload": workload_name(spec), "full_cover": args.full_cover, "tile_size": 16, "semantics": "ref_cpu",
                    "sort_mode": "split" if split else "full", "views_per_rank": K, "parallelism": f"view-sharded x{world}",
                    "frames_in_flight": F, "repeats": R,
+                   "submission": (f"{sum(int(i.graph_launch) for i in infos)} of {len(infos)} timed frames went out as ONE "
+                                  "CUDA graph launch each (captured from the library's own launch sequence, arguments "
+                                  "updated in place); gpu_launches counts the kernels inside them"),
                    "ms_per_step_p10_p50_p90": [round(pct(ms_dev_rep, q) / K, 5) for q in (0.1, 0.5, 0.9)],
                    "l2": ("256 MiB written before every frame, inside the timed region" if explicit_flush else
                           f"inputs larger than L2: {F} contexts, each with its own {56 * spec.n / 1e6:.0f} MB copy of the "
