@@ -287,7 +287,7 @@ def run_ours(args):
     from intro_to_gaussian_splatting_b200 import Rasterizer, _lib
     from intro_to_gaussian_splatting_b200.colmap_io import read_camera_file, read_image_file
     from intro_to_gaussian_splatting_b200.image import GaussianImage
-    from intro_to_gaussian_splatting_b200.sharding import ViewShard, broadcast_gaussians
+    from intro_to_gaussian_splatting_b200.sharding import ViewShard, broadcast_gaussians, gather_frames
     from intro_to_gaussian_splatting_b200.synth import CONFIGS, make_scene, write_colmap_text
 
     rank = int(os.environ.get("RANK", "0"))
@@ -493,6 +493,28 @@ def run_ours(args):
                     if hashlib.sha256(img.cpu().numpy().tobytes()).hexdigest() != digest:
                         frames_identical = False
 
+    # optional egress: every rank's first frame gathered on rank 0 as device tensors over
+    # NCCL (sharding.gather_frames), compared there with rank 0's own render of the same view; outside the timed region
+    gather_check = None
+    if world > 1:
+        one_each = ViewShard(world, rank, world)  # "view" r of this shard = rank r's first timed view
+        rast.render(cams[views[0]], prm, out=img)
+        torch.cuda.synchronize()
+        first_views = [None] * world
+        dist.all_gather_object(first_views, views[0])
+        t0 = time.perf_counter()
+        got = gather_frames([img], one_each)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if rank == 0:
+            same = True
+            for r_, v in enumerate(first_views):
+                rast.render(cams[v], prm, out=img)
+                torch.cuda.synchronize()
+                same = same and bool(torch.equal(img, got[r_]))
+            gather_check = {"frames_equal_rank0_render": same, "seconds": round(dt, 4),
+                            "mb": round(world * img.numel() * 4 / 1e6, 1)}
+
     # the training step, outside the headline's timed region: forward with
     # save_for_backward + gsb_render_backward for a random dL/d image, serial frames, L2 flushed before each
     prm_b = _lib.default_params(full_cover=args.full_cover, sort_mode=prm.sort_mode, save_for_backward=1)
@@ -642,6 +664,7 @@ def run_ours(args):
                    "gaussian_broadcast_note": "first call includes NCCL communicator bring-up; the second one is the "
                                               f"{56 * spec.n / 1e6:.0f} MB transfer on the warm communicator",
                    "frames_identical": frames_identical,
+                   "gather_frames_nccl": gather_check,
                    "host": dict(host_topology(), cpus_bound_per_rank=numa)},
         "e2e": {"value": fps(ms_e2e), "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": C.sizeof(_lib.GsbCamera) + C.sizeof(_lib.GsbParams),

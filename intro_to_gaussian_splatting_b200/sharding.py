@@ -80,16 +80,22 @@ def allreduce_gradients(grads: Sequence[Optional[torch.Tensor]], world: int, ave
 
 
 def gather_frames(frames: Sequence[torch.Tensor], shard: ViewShard) -> Optional[List[torch.Tensor]]:
-    """Optional egress: collect the per-rank frames on rank 0 in view order (not part of the fps metric)."""
+    """Optional egress (not part of the fps metric): collect the per-rank frames of one
+    image size on rank 0, in view order.  ONE tensor gather -- the frames stay where they are (device tensors travel
+    over NVLink with NCCL, CPU tensors with gloo), nothing is pickled.  `frames` are this rank's frames in the order
+    of `shard.my_views()`; ranks with one view fewer pad their block.  Returns the list on rank 0, None elsewhere."""
     if shard.world == 1:
         return list(frames)
-    lst = [None] * shard.world if shard.rank == 0 else None
-    dist.gather_object([f.cpu() for f in frames], lst, dst=0)
+    if len(frames) != len(shard.my_views()):
+        raise RuntimeError("gather_frames: one frame per view of shard.my_views() expected")
+    per_rank = (shard.n_views + shard.world - 1) // shard.world
+    if per_rank == 0:
+        return [] if shard.rank == 0 else None
+    if len(frames) == 0:
+        raise RuntimeError("gather_frames: a rank without views cannot describe the frame shape; use n_views >= world")
+    block = torch.stack(list(frames) + [torch.zeros_like(frames[0])] * (per_rank - len(frames)))
+    parts = [torch.empty_like(block) for _ in range(shard.world)] if shard.rank == 0 else None
+    dist.gather(block, parts, dst=0)
     if shard.rank != 0:
         return None
-    n = sum(len(x) for x in lst)
-    out = [None] * n
-    for r, fr in enumerate(lst):
-        for i, f in enumerate(fr):
-            out[i * shard.world + r] = f
-    return out
+    return [parts[v % shard.world][v // shard.world] for v in range(shard.n_views)]
