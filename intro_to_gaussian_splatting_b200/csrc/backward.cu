@@ -35,6 +35,7 @@ constexpr int kG2 = 12;  // floats per row of grad2d
 
 struct BwdArgs {
   int width, height, tiles_x, tiles_y;
+  float cull_log2;  // log2 of GsbParams.cull_alpha as the forward kernel used it (-inf: no culling)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -74,6 +75,10 @@ __device__ __forceinline__ float single_step(float x, int bit) { return x + __sh
 // The nine per-Gaussian sums of a warp are reduced with a 12-shuffle butterfly (pair_step), stored to the warp's
 // row of a shared accumulator, and after each batch of 128 Gaussians the two warps' rows are added into grad2d
 // with three vector reductions per Gaussian (REDG.ADD.F32x4 x2 + one scalar) instead of 18 scalar atomics.
+// A warp walks only the records the forward kernel's warp walked: the same conservative bound of alpha over the
+// warp's 16x8 pixels (may_contribute, gsb_internal.cuh; same inputs, same threshold) is evaluated once per record and
+// warp rectangle when a batch has landed, the survivors are compacted into a per-warp slot list, and the skipped
+// records get exactly the zero gradient their skipped forward step implies.
 __global__ void __launch_bounds__(kBwdThreads)
 composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
                           const float4* __restrict__ rec, const float* __restrict__ grad_image,
@@ -83,6 +88,8 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
   __shared__ uint32_t sm_idx[2][kBwdBatch];
   __shared__ float sm_acc[2][kBwdBatch * 9];  // [warp][slot][value]; zero except between a batch and its flush
   __shared__ uint32_t sm_nmax[2];
+  __shared__ __align__(16) uint32_t sm_mask[2][kBwdBatch / 32];  // [warp rectangle][survivor bits of the batch]
+  __shared__ uint8_t sm_list[2][kBwdBatch];                      // per warp: surviving slots, ascending
 
   const int tile = blockIdx.x;
   const int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
@@ -90,6 +97,10 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
   const int px = tx * kTile + (lane & 15);
   const int py0 = ty * kTile + warp * 8 + (lane >> 4) * 4;
   const float fx = (float)px;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float rx0 = (float)(tx * kTile), rx1 = rx0 + 15.f;
+  const float ry0 = (float)(ty * kTile), ry1 = ry0 + 7.f, ry2 = ry0 + 8.f, ry3 = ry0 + 15.f;
+  const bool cull_on = a.cull_log2 > -INFINITY;
 
   const uint2 rg = ranges[tile];
   const uint32_t len = rg.y - rg.x;
@@ -164,6 +175,46 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
     // this warp's slots of the batch: [0, hi)
     const int base = b * kBwdBatch;
     const int hi = min((int)nw - base, kBwdBatch);
+    // survivors of the batch per warp rectangle: slot j*64 + tid is bit `lane` of word 2j + warp
+    {
+      const int hi0 = (int)sm_nmax[0] - base, hi1 = (int)sm_nmax[1] - base;
+#pragma unroll
+      for (int j = 0; j < kBwdPerThread; ++j) {
+        const int s = j * kBwdThreads + tid;
+        const bool have = sm_idx[buf][s] != 0xFFFFFFFFu;
+        bool k0 = have && s < hi0, k1 = have && s < hi1;
+        if (cull_on && (k0 || k1)) {
+          const float4 q0 = sm[buf][s * 3], q1 = sm[buf][s * 3 + 1];
+          const float dxl = q0.x - rx1, dxh = q0.x - rx0;
+          if (k0) k0 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry1, q0.y - ry0, a.cull_log2);
+          if (k1) k1 = may_contribute(q0.z, q0.w, q1.x, q1.y, q1.z, dxl, dxh, q0.y - ry3, q0.y - ry2, a.cull_log2);
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+        if (lane == 0) { sm_mask[0][2 * j + warp] = m0; sm_mask[1][2 * j + warp] = m1; }
+      }
+    }
+    __syncthreads();  // masks visible
+    const uint4 mk = *reinterpret_cast<const uint4*>(sm_mask[warp]);
+    const int p1 = __popc(mk.x), p2 = p1 + __popc(mk.y), p3 = p2 + __popc(mk.z), total = p3 + __popc(mk.w);
+    {
+      uint8_t* lst = sm_list[warp];
+      if ((mk.x >> lane) & 1u) lst[__popc(mk.x & lt_mask)] = (uint8_t)lane;
+      if ((mk.y >> lane) & 1u) lst[p1 + __popc(mk.y & lt_mask)] = (uint8_t)(32 + lane);
+      if ((mk.z >> lane) & 1u) lst[p2 + __popc(mk.z & lt_mask)] = (uint8_t)(64 + lane);
+      if ((mk.w >> lane) & 1u) lst[p3 + __popc(mk.w & lt_mask)] = (uint8_t)(96 + lane);
+    }
+    __syncwarp();
+    // entries of the list below `sel_lo` sit under the warp's minimum blended length: no per-pixel masking there
+    int sel_lo;
+    {
+      const int smin = min(max((int)nmin_w - base, 0), kBwdBatch);  // slots >= smin need the per-pixel test
+      auto below = [&](uint32_t m, int w) {  // set bits of word w at slots < smin
+        const int r = smin - 32 * w;
+        return r <= 0 ? 0 : (r >= 32 ? __popc(m) : __popc(m & ((1u << r) - 1u)));
+      };
+      sel_lo = below(mk.x, 0) + below(mk.y, 1) + below(mk.z, 2) + below(mk.w, 3);
+    }
+    (void)hi;
     // one Gaussian (slot i of the batch) against the thread's four pixels; kSel: some pixel of the warp stopped
     // blending before this Gaussian, so alpha is masked per pixel (warp-uniformly false below the warp's minimum)
     auto step = [&](int i, auto sel_tag) {
@@ -205,9 +256,9 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
       d0 = single_step(d0, 1);
       if (v_writer) my_acc[i * 9] = d0;
     };
-    int i = hi - 1;
-    for (; i >= 0 && base + i >= (int)nmin_w; --i) step(i, std::true_type{});
-    for (; i >= 0; --i) step(i, std::false_type{});
+    int n = total - 1;
+    for (; n >= sel_lo; --n) step((int)sm_list[warp][n], std::true_type{});
+    for (; n >= 0; --n) step((int)sm_list[warp][n], std::false_type{});
     __syncthreads();  // both warps are done with the batch: flush its sums
 #pragma unroll
     for (int jj = 0; jj < kBwdPerThread; ++jj) {
@@ -432,7 +483,7 @@ int launch_composite_backward(const uint2* ranges, const uint32_t* payload, cons
   (void)prm;
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
-  BwdArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y};
+  BwdArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, cull_threshold_log2(prm)};
   composite_backward_kernel<<<tiles, kBwdThreads, 0, st>>>(ranges, payload, rec, grad_image, aux_t, aux_n, grad2d, a);
   return (int)cudaGetLastError();
 }

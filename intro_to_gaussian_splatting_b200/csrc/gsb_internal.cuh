@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 
 #include "../../include/gsb.h"
 
@@ -174,6 +175,46 @@ struct TileSource {
 // once when it is set (see kCtlAbort).
 int launch_composite(const TileSource& src, const float4* rec, float* image, FrameGeom geom, const GsbParams& prm,
                      float* aux_t, uint32_t* aux_n, const uint32_t* abort, cudaStream_t st);
+
+// ---- warp-level culling, shared by the compositing kernel and its gradient pass (both must skip the same records) ----
+// log2 of GsbParams.cull_alpha as the kernels use it
+inline float cull_threshold_log2(const GsbParams& prm) {
+  // cull_alpha < 0: no warp-level skipping; 0: skip only what is exactly zero in fp32 (ex2.approx.ftz flushes below
+  // 2^-126; one binade of slack for its own rounding); > 0: skip when every alpha of the warp is below it
+  if (prm.cull_alpha < 0.f) return -INFINITY;
+  if (prm.cull_alpha == 0.f) return -127.f;
+  const float l = log2f(prm.cull_alpha);
+  return l < -127.f ? -127.f : l;
+}
+#ifdef __CUDACC__
+// max over t in [lo, hi] of  q t^2 + s t + c0  for q < 0;  rq = 1 / (2 q)
+__device__ __forceinline__ float edge_max(float q, float s, float lo, float hi, float rq, float c0) {
+  const float t = fminf(fmaxf(-s * rq, lo), hi);
+  return fmaf(fmaf(q, t, s), t, c0);
+}
+
+// May any pixel of the rectangle dx in [dxl, dxh], dy in [dyl, dyh] (offsets mean - pixel) see
+// exp2(power * log2e + l2op) >= 2^thr ?  (A B; C D) = -0.5 * inverse covariance.  Conservative: answers true
+// whenever it cannot prove otherwise (indefinite or non-finite conic, NaNs, large cancellation).
+__device__ __forceinline__ bool may_contribute(float A, float B, float C, float D, float l2op, float dxl, float dxh,
+                                               float dyl, float dyh, float thr) {
+  const float S = B + C;
+  const bool ok = A < 0.f && A > -1e30f && D < 0.f && D > -1e30f && fmaf(4.f * A, D, -S * S) > 0.f &&
+                  fabsf(dxl) < 1e30f && fabsf(dyl) < 1e30f;
+  const bool inside = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;
+  const float rA = __frcp_rn(2.f * A), rD = __frcp_rn(2.f * D);
+  const float g1 = edge_max(D, S * dxl, dyl, dyh, rD, A * dxl * dxl);
+  const float g2 = edge_max(D, S * dxh, dyl, dyh, rD, A * dxh * dxh);
+  const float h1 = edge_max(A, S * dyl, dxl, dxh, rA, D * dyl * dyl);
+  const float h2 = edge_max(A, S * dyh, dxl, dxh, rA, D * dyh * dyh);
+  const float ub = inside ? 0.f : fmaxf(fmaxf(g1, g2), fmaxf(h1, h2));
+  const float ax = fmaxf(fabsf(dxl), fabsf(dxh)), ay = fmaxf(fabsf(dyl), fabsf(dyh));
+  // |rounding error| of the fp32 evaluation in the blend loop (and of this bound) <= 2^-21 * sum of |terms|
+  const float mag = fmaf(fabsf(A) * ax, ax, fmaf((fabsf(B) + fabsf(C)) * ax, ay, fabsf(D) * ay * ay));
+  const float arg = fmaf(ub + fmaf(mag, 4.76837158e-7f, 1e-3f), 1.4426950408889634f, l2op);
+  return !ok || !(arg < thr);
+}
+#endif  // __CUDACC__
 
 // ---- backward pass (backward.cu) ----
 // grad2d: 12 zeroed floats per Gaussian row: d mean x,y | d a, d (b+c), d d (a b; c d = -0.5 inverse covariance) |
