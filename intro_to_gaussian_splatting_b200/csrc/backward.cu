@@ -43,6 +43,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP; the operand here is 1 - alpha >= 0.01
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -79,6 +84,7 @@ __device__ __forceinline__ float single_step(float x, int bit) { return x + __sh
 // warp's 16x8 pixels (may_contribute, gsb_internal.cuh; same inputs, same threshold) is evaluated once per record and
 // warp rectangle when a batch has landed, the survivors are compacted into a per-warp slot list, and the skipped
 // records get exactly the zero gradient their skipped forward step implies.
+template <bool kCull>
 __global__ void __launch_bounds__(kBwdThreads)
 composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ payload,
                           const float4* __restrict__ rec, const float* __restrict__ grad_image,
@@ -100,7 +106,7 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
   const unsigned lt_mask = (1u << lane) - 1u;
   const float rx0 = (float)(tx * kTile), rx1 = rx0 + 15.f;
   const float ry0 = (float)(ty * kTile), ry1 = ry0 + 7.f, ry2 = ry0 + 8.f, ry3 = ry0 + 15.f;
-  const bool cull_on = a.cull_log2 > -INFINITY;
+  constexpr bool cull_on = kCull;
 
   const uint2 rg = ranges[tile];
   const uint32_t len = rg.y - rg.x;
@@ -226,24 +232,30 @@ composite_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
       const float dx = q0.x - fx;
       const float bc = q0.w + q1.x;
       const float adx = q0.z * dx, bcdx = bc * dx, adxx = adx * dx;
-      float P0 = 0.f, P1 = 0.f, P2 = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f, amax = 0.f;
+      float P0, P1, P2, s_r, s_g, s_b, amax = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float dy = q0.y - fy[k];
         const float pw = fmaf(fmaf(q1.y, dy, bcdx), dy, adxx);  // a dx^2 + (b+c) dx dy + d dy^2
         float al = ex2_approx(fmaf(pw, 1.4426950408889634f, q1.z));
         if (kSel) al = (j < npx[k]) ? al : 0.f;  // not blended for this pixel: alpha = 0 makes every update a no-op
-        amax = fmaxf(amax, al);
-        T[k] = __fdividef(T[k], 1.f - al);  // T_j from T_{j+1}
+        if (!kCull) amax = fmaxf(amax, al);
+        T[k] *= rcp_approx(1.f - al);  // T_j from T_{j+1}
         const float w = al * T[k];
-        s_r = fmaf(w, gr[k], s_r); s_g = fmaf(w, gg[k], s_g); s_b = fmaf(w, gb[k], s_b);
         const float e = fmaf(q1.w, gr[k], fmaf(q2.x, gg[k], q2.y * gb[k])) - B[k];
         const float dpw = w * e;
         B[k] = fmaf(al, e, B[k]);
         const float t = dpw * dy;
-        P0 += dpw; P1 += t; P2 = fmaf(t, dy, P2);
+        if (k == 0) {  // (resolved at compile time: the first pixel starts the sums)
+          s_r = w * gr[0]; s_g = w * gg[0]; s_b = w * gb[0];
+          P0 = dpw; P1 = t; P2 = t * dy;
+        } else {
+          s_r = fmaf(w, gr[k], s_r); s_g = fmaf(w, gg[k], s_g); s_b = fmaf(w, gb[k], s_b);
+          P0 += dpw; P1 += t; P2 = fmaf(t, dy, P2);
+        }
       }
-      if (!__any_sync(0xffffffffu, amax != 0.f)) return;  // exp underflow everywhere: every sum is exactly zero
+      // without culling: exp underflow everywhere makes every sum exactly zero (with it such records never get here)
+      if (!kCull && !__any_sync(0xffffffffu, amax != 0.f)) return;
       const float s_a = dx * dx * P0, s_bc = dx * P1;
       const float s_mx = fmaf(bc, P1, 2.f * adx * P0);
       const float s_my = fmaf(bcdx, P0, 2.f * q1.y * P1);
@@ -484,7 +496,10 @@ int launch_composite_backward(const uint2* ranges, const uint32_t* payload, cons
   const int tiles = geom.tiles_x * geom.tiles_y;
   if (tiles <= 0) return 0;
   BwdArgs a{geom.width, geom.height, geom.tiles_x, geom.tiles_y, cull_threshold_log2(prm)};
-  composite_backward_kernel<<<tiles, kBwdThreads, 0, st>>>(ranges, payload, rec, grad_image, aux_t, aux_n, grad2d, a);
+  if (a.cull_log2 > -INFINITY)
+    composite_backward_kernel<true><<<tiles, kBwdThreads, 0, st>>>(ranges, payload, rec, grad_image, aux_t, aux_n, grad2d, a);
+  else
+    composite_backward_kernel<false><<<tiles, kBwdThreads, 0, st>>>(ranges, payload, rec, grad_image, aux_t, aux_n, grad2d, a);
   return (int)cudaGetLastError();
 }
 
