@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool racecheck python tools/sanitize_driver.py
 
-Both sort modes, both tile grids, forward with and without saved state, backward, the parity getters (which run
+Both sort modes, both tile grids, forward with and without saved state, backward, launch by launch and as a graph, the parity getters (which run
 expand_kernel and the key rebuild) and gsb_preprocess, on the `small` and `tiny` scenes."""
 import os
 import sys
@@ -26,6 +26,14 @@ for name, fc, mode in (("small", 1, _lib.GSB_SORT_SPLIT), ("small", 0, _lib.GSB_
         img = r.render(cam, prm)
         if save:
             r.render_backward(cam, prm, torch.ones_like(img))
+    side = torch.cuda.Stream()  # any stream but the default one: the frame goes out as one CUDA graph launch
+    with torch.cuda.stream(side):
+        for save in (0, 1):
+            prm = _lib.default_params(full_cover=fc, sort_mode=mode, save_for_backward=save)
+            img = r.render(cam, prm)
+            if save:
+                r.render_backward(cam, prm, torch.ones_like(img))
+    side.synchronize()
     r.debug_sorted_keys()
     r.debug_tile_ranges()
     pp = r.preprocess(cam)
