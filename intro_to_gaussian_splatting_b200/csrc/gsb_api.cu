@@ -97,7 +97,7 @@ CtlLayout ctl_layout(FrameGeom g, SuperGeom sg, int64_t n_rows, size_t dsort_wor
   L.grid = L.hist + kCtlHistWords;
   L.grid_s = up4(L.grid + (size_t)(g.tiles_x + 1) * (size_t)(g.tiles_y + 1));
   L.scan = up4(L.grid_s + (size_t)(sg.nx + 1) * (size_t)(sg.ny + 1));
-  L.dsort = up4(L.scan + scan_status_words(n_rows));
+  L.dsort = (L.scan + scan_status_words(n_rows) + 31) & ~(size_t)31;  // 128-byte aligned: see make_sort_plan
   L.total = up4(L.dsort + dsort_words);
   return L;
 }

@@ -36,6 +36,7 @@ namespace gsb {
 constexpr int kTile = 16;              // pixels per tile edge (the only size the kernels are built for)
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
+constexpr int kTicketWords = 32;  // head of a radix sort's control block: 8 pass tickets padded to a 128-byte line
 constexpr int kMaxPasses = 8;
 // words of the per-frame control header (zeroed once per frame)
 constexpr int kCtlM = 0;        // Gaussians in view
