@@ -166,6 +166,7 @@ struct GsbContext {
   bool have_order = false;
   int64_t frame_rows = 0;  // rows of the per-Gaussian arrays of the last frame (N, or M for gsb_render_image)
   int tail_reruns = 0;     // frames whose tail had to be queued twice (a count outgrew its buffer)
+  int64_t ks_hint = 0;     // super-tile instances of the last frame of this scene (0: none yet)
   GsbFrameInfo info{};
   cudaEvent_t ev[GSB_NUM_STAGES + 9]{};
   int mark_stage[GSB_NUM_STAGES + 9]{};
@@ -472,6 +473,12 @@ void read_capacities(GsbContext* c, SplitPlan& sp) {
   sp.cap_ks = cks < lim ? cks : lim;
 }
 
+// Keys per thread of the super-tile radix passes.  Around a million keys (config 3) the pass is a few hundred tiles
+// whose last pass gathers two records per key: 8 keys per thread (twice the CTAs) run it in 22.5 us instead of 28-32;
+// from a few million keys on 16 is as good or better (config 4: 45 vs 45 us) and halves the status words.  The count
+// is not known when the frame is queued: the last frame's stands in for it.
+int tile_sort_items(const GsbContext* c) { return (c->ks_hint > 0 && c->ks_hint <= (int64_t)2 << 20) ? 8 : 16; }
+
 int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const uint32_t* v_limit, FrameGeom geom,
                      const SplitPlan& sp, uint32_t* ctl, const CtlLayout& L, cudaStream_t st, StageTimer& tm,
                      int* launches) {
@@ -481,7 +488,7 @@ int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const 
   bool in_a = true;
   int passes = 0;
   if (sp.keys32) {
-    SortPlan plan = make_sort_plan<uint32_t>(sp.cap_ks, sp.rank_bits, sp.rank_bits + sp.sbits);
+    SortPlan plan = make_sort_plan<uint32_t>(sp.cap_ks, sp.rank_bits, sp.rank_bits + sp.sbits, tile_sort_items(c));
     plan.keys_only = 1;
     plan.low_bits = sp.rank_bits;
     plan.gather_table = perm;  // nullptr (pre-sorted rows): the position IS the row
@@ -499,7 +506,7 @@ int queue_split_tail(GsbContext* c, int64_t n_rows, const uint32_t* perm, const 
                                                     c->control2.as<uint32_t>(), &in_a, launches, st));
     passes = plan.passes;
   } else {
-    SortPlan plan = make_sort_plan<uint64_t>(sp.cap_ks, 32, 32 + sp.sbits);
+    SortPlan plan = make_sort_plan<uint64_t>(sp.cap_ks, 32, 32 + sp.sbits, tile_sort_items(c));
     plan.keys_only = 1;
     plan.n_dev = ctl + kCtlKs;
     plan.abort = abort;
@@ -601,6 +608,7 @@ int run_split(GsbContext* c, int64_t n_rows, const uint32_t* perm, bool rows_sor
   c->info.v_with_tiles = rows_sorted_by_visibility ? cn.v : 0;
   c->info.k_instances = cn.k;
   c->info.k_sorted = cn.ks;
+  c->ks_hint = cn.ks;
   if (cn.abort) {
     c->info.tail_requeued = 1;
     // a count outgrew its buffer: none of the tail kernels touched anything.  Grow (cudaFree drains the device),
@@ -812,8 +820,8 @@ int gsb_create(GsbContext** out, int device) {
   if (!c) return GSB_E_ALLOC;
   c->device = device;
   {  // process-wide tuning / test knobs, re-read whenever a context is created
-    const char* e = std::getenv("GSB_SORT_ITEMS");        // onesweep keys per thread: 16 (default) or 8
-    set_sort_items(e ? std::atoi(e) : 16);
+    const char* e = std::getenv("GSB_SORT_ITEMS");        // onesweep keys per thread, all sorts: 16 or 8 (unset: per sort)
+    set_sort_items(e ? std::atoi(e) : 0);
     e = std::getenv("GSB_FORCE_WIDE_STATUS");             // 1: 64-bit look-back words even below 2^30 keys
     set_force_wide_status(e ? std::atoi(e) : 0);
     e = std::getenv("GSB_KEYS32");                        // 0: never use 32-bit keys for the super-tile passes
@@ -875,6 +883,7 @@ int gsb_upload(GsbContext* c, int64_t n, const float* xyz, const float* scales, 
   c->frame_projected = false;
   c->have_saved = false;
   ++c->scene_gen;
+  c->ks_hint = 0;
   c->n = n;
   c->n_pad = (n + 3) & ~(int64_t)3;
   if (n == 0) return GSB_OK;

@@ -146,7 +146,7 @@ struct SortPlan {
 void set_sort_items(int items);
 void set_force_wide_status(int on);
 template <typename KeyT>
-SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit);
+SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit, int items = 16);
 // digit histograms computed from the keys (stand-alone sort only); hist = kMaxPasses*256 zeroed words
 template <typename KeyT>
 int launch_key_histogram(const SortPlan& plan, const KeyT* keys, uint32_t* hist, cudaStream_t st);

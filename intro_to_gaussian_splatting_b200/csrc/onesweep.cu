@@ -184,13 +184,16 @@ struct SortSmem {
   uint32_t tile;
 };
 
-// Opt-in phase clocks (-DGSB_PHASE_CLOCKS, tools/phase_clocks.py): thread 0 of every tile of the keys-only passes
+// Opt-in phase clocks (-DGSB_PHASE_CLOCKS, tools/phase_clocks.py): thread 0 of every tile of one pass flavour (GSB_PHASE_MODE)
 // adds the cycles between consecutive marks to g_phase[mark]; g_phase[15] counts tiles.  Off in the shipped library.
 #ifdef GSB_PHASE_CLOCKS
+#ifndef GSB_PHASE_MODE
+#define GSB_PHASE_MODE kKeysOnlyEntryOut  // which pass flavour is clocked: 0 = the depth sort's (key, payload) passes
+#endif
 __device__ unsigned long long g_phase[16];
 #define GSB_PHASE(k)                                                        \
   do {                                                                      \
-    if (kMode == kKeysOnly && threadIdx.x == 0) {                           \
+    if (kMode == GSB_PHASE_MODE && threadIdx.x == 0) {                      \
       const long long _t = clock64();                                       \
       atomicAdd(&g_phase[k], (unsigned long long)(_t - _t_prev));           \
       _t_prev = _t;                                                         \
@@ -221,7 +224,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
 
 #ifdef GSB_PHASE_CLOCKS
   long long _t_prev = clock64();
-  if (kMode == kKeysOnly && threadIdx.x == 0) atomicAdd(&g_phase[15], 1ull);
+  if (kMode == GSB_PHASE_MODE && threadIdx.x == 0) atomicAdd(&g_phase[15], 1ull);
 #endif
   // 2. warp-striped coalesced loads
   KeyT key[kItems];
@@ -382,7 +385,7 @@ __device__ __forceinline__ void onesweep_tile(SortSmem<KeyT, kItems>& sm, const 
       }
       SW::st(st, kWPre | (((W)excl + (W)real) & kWMask));
 #ifdef GSB_PHASE_CLOCKS
-      if (kMode == kKeysOnly && threadIdx.x == 0) { atomicAdd(&g_phase[8], n_words); atomicAdd(&g_phase[9], n_spins); }
+      if (kMode == GSB_PHASE_MODE && threadIdx.x == 0) { atomicAdd(&g_phase[8], n_words); atomicAdd(&g_phase[9], n_spins); }
 #endif
     }
     s_gofs[tid] = bin_base + excl - tile_start;  // global index = s_gofs[d] + local position (mod 2^32)
@@ -478,13 +481,14 @@ extern "C" int gsb_debug_phase_clocks(unsigned long long* out) {
   return (int)e;
 }
 #endif
-static int g_sort_items = 16;  // keys per thread of the onesweep tile (8 or 16); tuning knob, see gsb_api.cu
-void set_sort_items(int items) { g_sort_items = (items == 8) ? 8 : 16; }
+static int g_sort_items = 0;  // keys per thread of the onesweep tile forced by GSB_SORT_ITEMS (8 or 16); 0: per sort
+void set_sort_items(int items) { g_sort_items = (items == 8 || items == 16) ? items : 0; }
 static int g_force_wide = 0;   // test knob: use the 64-bit look-back words regardless of the key count
 void set_force_wide_status(int on) { g_force_wide = on ? 1 : 0; }
 
+// items: keys per thread (8 or 16) the caller would like; GSB_SORT_ITEMS overrides it for every sort
 template <typename KeyT>
-SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
+SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit, int items) {
   SortPlan p;
   p.begin_bit = begin_bit;
   p.end_bit = end_bit;
@@ -499,7 +503,7 @@ SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
   p.entry_rect = nullptr;
   p.entry_lw = p.entry_lh = 0;
   p.entry_snx = 1;
-  p.items = g_sort_items;
+  p.items = g_sort_items ? g_sort_items : (items == 8 ? 8 : 16);
   const int64_t tile_keys = (int64_t)kThreads * p.items;
   p.tiles = (n + tile_keys - 1) / tile_keys;
   // [tickets: 8, padded to one 128-byte line][status: passes * tiles * 256 words; 64-bit words from 2^30 keys on].
@@ -509,8 +513,8 @@ SortPlan make_sort_plan(int64_t n, int begin_bit, int end_bit) {
   p.control_words = kTicketWords + (size_t)p.passes * (size_t)p.tiles * kRadix * (p.wide_status ? 2 : 1);
   return p;
 }
-template SortPlan make_sort_plan<uint32_t>(int64_t, int, int);
-template SortPlan make_sort_plan<uint64_t>(int64_t, int, int);
+template SortPlan make_sort_plan<uint32_t>(int64_t, int, int, int);
+template SortPlan make_sort_plan<uint64_t>(int64_t, int, int, int);
 
 // Histogram of the keys themselves (only the stand-alone sort entry needs it; the frame pipeline gets its
 // histograms from the projection kernel and tile_stats_kernel).  hist: kMaxPasses*256 zeroed words.

@@ -1,6 +1,6 @@
 """Phase clocks of the radix pass (not a benchmark): builds libgsb_b200 with -DGSB_PHASE_CLOCKS into a scratch
 directory, renders a few config-3 frames with it and prints, per frame, the mean cycles thread 0 of a tile spends
-between the marks of csrc/onesweep.cu (8-bit keys-only tile pass).  The shipped library is not touched.
+between the marks of csrc/onesweep.cu (the tile pass; PHASE_MODE=0: the four depth-sort passes).  The shipped library is not touched.
 
     python tools/phase_clocks.py            # on a B200 box
 """
@@ -15,6 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CSRC = os.path.join(ROOT, "intro_to_gaussian_splatting_b200", "csrc")
 
+# PHASE_MODE=0 clocks the depth sort's (key, payload) passes; default: the tile pass (keys only, entry out)
+MODE = ["-DGSB_PHASE_MODE=" + os.environ["PHASE_MODE"]] if os.environ.get("PHASE_MODE") else []
 work = tempfile.mkdtemp(prefix="gsb_phase_")
 objs = []
 for name in ("project", "binning", "onesweep", "composite", "backward", "gsb_api"):
@@ -23,7 +25,7 @@ for name in ("project", "binning", "onesweep", "composite", "backward", "gsb_api
         extra += ["-prec-div=true", "-prec-sqrt=true"]
     obj = os.path.join(work, name + ".o")
     subprocess.run(["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin",
-                    "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2", "-DGSB_PHASE_CLOCKS", *extra, "-c",
+                    "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2", "-DGSB_PHASE_CLOCKS", *MODE, *extra, "-c",
                     os.path.join(CSRC, name + ".cu"), "-o", obj], check=True)
     objs.append(obj)
 lib_path = os.path.join(work, "libgsb_b200.so")
